@@ -1,0 +1,99 @@
+"""Build recipes.
+
+  build_product()  nvcc -> imageworsener_b200/libimagew_b200.so   (sm_100a only; the shipped library)
+  build_emulator() g++  -> tests/_emu/libimagew_emu.so            (TEST-ONLY host emulation of the kernel bodies,
+                                                                   used to debug host logic on a GPU-less box;
+                                                                   never imported by the package or the bench)
+  build_oracle()   make -C oracle (C restatement + oracle/_ref when /root/reference is present)
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+PRODUCT_SO = os.path.join(HERE, "libimagew_b200.so")
+EMU_DIR = os.path.join(ROOT, "tests", "_emu")
+EMU_SO = os.path.join(EMU_DIR, "libimagew_emu.so")
+
+HOST_SOURCES = ["api.cpp", "plan.cpp", "weights.cpp", "tables.cpp", "process.cpp"]
+DEVICE_SOURCES = ["pipeline.cu"]
+
+
+def _newer(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def _all_deps() -> list[str]:
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(ROOT, "include", "imagew_b200.h"))
+    deps.append(os.path.abspath(__file__))
+    return deps
+
+
+def _run(cmd: list[str]) -> None:
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("build failed: " + cmd[0])
+    if r.stderr.strip() and os.environ.get("IWB_BUILD_VERBOSE"):
+        sys.stderr.write(r.stderr)
+
+
+def nvcc_path() -> str:
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found")
+    return p
+
+
+def build_product(force: bool = False, verbose_ptxas: bool = False) -> str:
+    if not force and _newer(PRODUCT_SO, _all_deps()):
+        return PRODUCT_SO
+    srcs = [os.path.join(CSRC, f) for f in HOST_SOURCES + DEVICE_SOURCES]
+    cmd = [nvcc_path(), "-std=c++17", "-O3", "-lineinfo",
+           "-gencode", "arch=compute_100a,code=sm_100a",
+           "-fmad=false",                      # parity: the reference never fuses multiply-add
+           "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-Wall",
+           "-cudart", "static", "-shared",
+           "-Xlinker", "-Bsymbolic",
+           "-DIWB_BUILDING=1",
+           "-o", PRODUCT_SO] + srcs
+    if verbose_ptxas:
+        cmd.insert(1, "-Xptxas=-v")
+    _run(cmd)
+    return PRODUCT_SO
+
+
+def build_emulator(force: bool = False) -> str:
+    if not force and _newer(EMU_SO, _all_deps()):
+        return EMU_SO
+    os.makedirs(EMU_DIR, exist_ok=True)
+    srcs = [os.path.join(CSRC, f) for f in HOST_SOURCES]
+    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden",
+           "-Wl,-Bsymbolic", "-DIWB_EMU=1", "-DIWB_BUILDING=1", "-Wall", "-o", EMU_SO] + srcs
+    for f in DEVICE_SOURCES:
+        cmd += ["-x", "c++", os.path.join(CSRC, f)]
+    _run(cmd)
+    return EMU_SO
+
+
+def build_oracle() -> None:
+    _run(["make", "-C", os.path.join(ROOT, "oracle"), "all"])
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["product", "emulator", "oracle"]
+    if "product" in what:
+        print(build_product(force=True, verbose_ptxas="-v" in what))
+    if "emulator" in what:
+        print(build_emulator(force=True))
+    if "oracle" in what:
+        build_oracle()

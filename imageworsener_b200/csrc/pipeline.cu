@@ -1,0 +1,649 @@
+// pipeline.cu -- jobs: turn a prepared context into device tables and launch the kernels.
+//
+// Data layout in HBM: the input image is kept exactly as the caller stores it (interleaved,
+// caller's row stride, big-endian 16-bit); the FP32 intermediate of the vertical pass is one row-major plane per
+// channel covering only the current chunk of output rows, sized to stay resident in the 126 MB L2 between the
+// vertical pass that writes it and the horizontal pass that reads it; the output is written in its final
+// interleaved byte layout.  Chunks are processed in order on one stream.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "iwb_internal.h"
+#include "kernels.cuh"
+#if !defined(IWB_EMU)
+#include "fused.cuh"
+#endif
+
+// ------------------------------------------------------------------------------------------------------
+// Thin device layer.  The product build is CUDA only.  -DIWB_EMU (tests/_emu, never shipped, never loaded by the
+// package) swaps it for plain host memory + a loop so host logic can be debugged on a machine without a GPU.
+// ------------------------------------------------------------------------------------------------------
+static unsigned long long g_launches = 0;
+
+#if !defined(IWB_EMU)
+#include <cuda_runtime.h>
+typedef cudaStream_t iwb_stream;
+static const char *dev_check(cudaError_t e) { return e == cudaSuccess ? nullptr : cudaGetErrorString(e); }
+static void *dev_alloc(size_t n, std::string &err) {
+  void *p = nullptr;
+  if (const char *m = dev_check(cudaMalloc(&p, n ? n : 1))) { err = std::string("cudaMalloc: ") + m; return nullptr; }
+  return p;
+}
+static void dev_free(void *p) { if (p) cudaFree(p); }
+static bool dev_h2d(void *d, const void *h, size_t n, iwb_stream s, std::string &err) {
+  if (const char *m = dev_check(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s))) { err = std::string("H2D copy: ") + m; return false; }
+  return true;
+}
+static bool dev_d2h(void *h, const void *d, size_t n, iwb_stream s, std::string &err) {
+  if (const char *m = dev_check(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s))) { err = std::string("D2H copy: ") + m; return false; }
+  return true;
+}
+static bool dev_zero(void *d, size_t n, iwb_stream s) { return cudaMemsetAsync(d, 0, n, s) == cudaSuccess; }
+static bool dev_sync(iwb_stream s, std::string &err) {
+  if (const char *m = dev_check(cudaStreamSynchronize(s))) { err = std::string("kernel execution: ") + m; return false; }
+  return true;
+}
+template <class Body, class P>
+__global__ void iwb_thread_per_item(const P p, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) Body::run(p, i);
+}
+template <class Body, class P>
+__global__ void iwb_block_per_item(const P p) {
+  if (threadIdx.x == 0) Body::run(p, (size_t)blockIdx.x);
+}
+template <class Body, class P>
+static void launch(const P &p, size_t n, iwb_stream s) {
+  if (!n) return;
+  const int block = 256;
+  iwb_thread_per_item<Body, P><<<(unsigned)((n + block - 1) / block), block, 0, s>>>(p, n);
+  g_launches++;
+}
+template <class Body, class P>
+static void launch_serial(const P &p, int n, iwb_stream s) {  // n independent sequential chains
+  if (!n) return;
+  iwb_block_per_item<Body, P><<<n, 32, 0, s>>>(p);
+  g_launches++;
+}
+static bool dev_select(int device, std::string &err) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) {
+    err = "no CUDA device available (this library has no CPU path)";
+    return false;
+  }
+  if (device < 0 || device >= count) { err = "invalid CUDA device ordinal"; return false; }
+  if (const char *m = dev_check(cudaSetDevice(device))) { err = std::string("cudaSetDevice: ") + m; return false; }
+  return true;
+}
+#else
+typedef void *iwb_stream;
+static void *dev_alloc(size_t n, std::string &) { return malloc(n ? n : 1); }
+static void dev_free(void *p) { free(p); }
+static bool dev_h2d(void *d, const void *h, size_t n, iwb_stream, std::string &) { memcpy(d, h, n); return true; }
+static bool dev_d2h(void *h, const void *d, size_t n, iwb_stream, std::string &) { memcpy(h, d, n); return true; }
+static bool dev_zero(void *d, size_t n, iwb_stream) { memset(d, 0, n); return true; }
+static bool dev_sync(iwb_stream, std::string &) { return true; }
+template <class Body, class P>
+static void launch(const P &p, size_t n, iwb_stream) { for (size_t i = 0; i < n; i++) Body::run(p, i); g_launches++; }
+template <class Body, class P>
+static void launch_serial(const P &p, int n, iwb_stream) { for (int i = 0; i < n; i++) Body::run(p, (size_t)i); g_launches++; }
+static bool dev_select(int, std::string &) { return true; }
+#endif
+
+bool iwb_bkgd_is_translucent(const iw_context *ctx);  // plan.cpp
+
+// ------------------------------------------------------------------------------------------------------
+struct iwb200_job {
+  iw_context *ctx = nullptr;
+  int device = 0;
+  std::string err;
+  std::vector<void *> allocs;
+
+  int nproc = 0;             // intermediate channels in processing order (alpha first)
+  int mid_index[4] = {0, 0, 0, 0};
+  DevChanIn cin[4];
+  DevChanOut cout[4];
+  DevAxis vax[4], hax[4];
+  std::vector<iwb_axis_table> vtab, htab;   // host copies (band planning)
+  int vtab_of[4] = {0, 0, 0, 0};
+  DevCommon cm{};
+  DevInput in{};
+  DevOutput out{};
+  int in_w = 0, in_h = 0;    // cropped logical input size = axis inputs
+  int phys_w = 0, phys_h = 0;
+  int has_alpha = 0, any_random = 0, any_errdiff = 0;
+  int negate = 0, clear_transparent = 0, out_alpha_ch = -1;
+  iwb_affine_t *d_jump = nullptr;
+  double errdiff_m[4][12];
+  iwb200_job_info info{};
+
+  // scratch, sized for `chunk_rows` output rows
+  int chunk_rows = 0;
+  float *inter[4] = {nullptr, nullptr, nullptr, nullptr};
+  float *final_alpha = nullptr;
+  double *lin_plane[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint32_t *draws[4] = {nullptr, nullptr, nullptr, nullptr};
+  double *errrows[4] = {nullptr, nullptr, nullptr, nullptr};
+  int errdiff_next_row = 0;
+  // staging for run_host
+  void *d_in = nullptr; size_t d_in_bytes = 0;
+  void *d_out = nullptr; size_t d_out_bytes = 0;
+#if !defined(IWB_EMU)
+  FusedPlan fused;
+#endif
+
+  template <class T>
+  T *upload(const T *h, size_t count) {
+    void *d = dev_alloc(count * sizeof(T), err);
+    if (!d) return nullptr;
+    allocs.push_back(d);
+    if (count && !dev_h2d(d, h, count * sizeof(T), 0, err)) return nullptr;
+    return (T *)d;
+  }
+  void *scratch(size_t bytes) {
+    void *d = dev_alloc(bytes, err);
+    if (d) allocs.push_back(d);
+    return d;
+  }
+};
+
+namespace {
+
+bool fail(iwb200_job *job, const std::string &m) {
+  if (job->err.empty()) job->err = m;
+  return false;
+}
+
+bool upload_axis(iwb200_job *job, const iwb_axis_table &t, DevAxis *d) {
+  d->mode = t.mode;
+  d->n_in = t.n_in;
+  d->n_out = t.n_out;
+  d->edge_value = t.edge_value;
+  d->first = d->src = d->map = nullptr;
+  d->w = nullptr;
+  if (t.mode == 1) {
+    d->map = job->upload(t.map.data(), t.map.size());
+    return d->map != nullptr;
+  }
+  d->first = job->upload(t.first.data(), t.first.size());
+  d->src = job->upload(t.src.data(), t.src.size());
+  d->w = job->upload(t.w.data(), t.w.size());
+  return d->first && d->src && d->w;
+}
+
+// code -> linear table for one physical input channel (see kernels.cuh one_linear)
+struct lut_key { int maxcode, cstype; double gamma; const double *dev; };
+
+const double *input_lut(iwb200_job *job, std::vector<lut_key> &cache, int depth, int maxcode, const iw_csdescr &cs) {
+  for (auto &k : cache)
+    if (k.maxcode == maxcode && k.cstype == cs.cstype && (cs.cstype != IW_CSTYPE_GAMMA || k.gamma == cs.gamma)) return k.dev;
+  const int n = 1 << depth;
+  std::vector<double> t(n);
+  const double mx = (double)maxcode;
+  for (int i = 0; i < n; i++) t[i] = iwb_to_linear(((double)i) / mx, &cs);
+  const double *d = job->upload(t.data(), t.size());
+  cache.push_back({maxcode, cs.cstype, cs.gamma, d});
+  return d;
+}
+
+const double kErrDiff[8][12] = {  // x 0 1 / 2 3 4 5 6 / 7 8 9 10 11  (reference: src/imagew-main.c:506-535)
+    {7.0 / 16, 0.0, 0.0, 3.0 / 16, 5.0 / 16, 1.0 / 16, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {7.0 / 48, 5.0 / 48, 3.0 / 48, 5.0 / 48, 7.0 / 48, 5.0 / 48, 3.0 / 48, 1.0 / 48, 3.0 / 48, 5.0 / 48, 3.0 / 48, 1.0 / 48},
+    {8.0 / 42, 4.0 / 42, 2.0 / 42, 4.0 / 42, 8.0 / 42, 4.0 / 42, 2.0 / 42, 1.0 / 42, 2.0 / 42, 4.0 / 42, 2.0 / 42, 1.0 / 42},
+    {8.0 / 32, 4.0 / 32, 2.0 / 32, 4.0 / 32, 8.0 / 32, 4.0 / 32, 2.0 / 32, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {5.0 / 32, 3.0 / 32, 2.0 / 32, 4.0 / 32, 5.0 / 32, 4.0 / 32, 2.0 / 32, 0.0, 2.0 / 32, 3.0 / 32, 2.0 / 32, 0.0},
+    {4.0 / 16, 3.0 / 16, 1.0 / 16, 2.0 / 16, 3.0 / 16, 2.0 / 16, 1.0 / 16, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {2.0 / 4, 0.0, 0.0, 1.0 / 4, 1.0 / 4, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {1.0 / 8, 1.0 / 8, 0.0, 1.0 / 8, 1.0 / 8, 1.0 / 8, 0.0, 0.0, 0.0, 1.0 / 8, 0.0, 0.0}};
+
+bool build_output_tables(iwb200_job *job, const iw_context *ctx, const iwb_out_channel &oc, const iw_csdescr &cs,
+                         DevChanOut *o) {
+  // rev[k] = linear value of stored code k (reference: cvt_int_sample_to_linear_output, main.c:330-344)
+  const int maxcode = oc.maxcode;
+  const double mx = (double)maxcode;
+  std::vector<double> thr, code, lin;
+  if (oc.color_count == 0) {
+    thr.resize(maxcode + 1);
+    code.resize(maxcode + 1);
+    for (int k = 0; k <= maxcode; k++) {
+      thr[k] = iwb_to_linear(((double)k) / mx, &cs);
+      code[k] = (double)k;
+    }
+    lin = thr;
+  } else {
+    // posterised levels q = 0..cc-1 (reference: get_nearest_valid_colors, main.c:596-616)
+    const int cc = oc.color_count;
+    const double pm = (double)(cc - 1);
+    thr.resize(cc); code.resize(cc); lin.resize(cc);
+    for (int q = 0; q < cc; q++) {
+      thr[q] = iwb_to_linear(((double)q) / pm, &cs);
+      code[q] = floor(0.5000000001 + ((double)q) * (mx / pm));
+      lin[q] = iwb_to_linear(((double)(unsigned int)code[q]) / mx, &cs);
+    }
+  }
+  o->ntab = (int)thr.size();
+  o->thr = job->upload(thr.data(), thr.size());
+  o->codeval = job->upload(code.data(), code.size());
+  o->linval = job->upload(lin.data(), lin.size());
+  (void)ctx;
+  return o->thr && o->codeval && o->linval;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *iwb200_version(void) {
+#if defined(IWB_EMU)
+  return "imagew_b200 0.1 host-emulation (test build, not the product)";
+#else
+  return "imagew_b200 0.1 sm_100a";
+#endif
+}
+unsigned long long iwb200_kernel_launch_count(void) { return g_launches; }
+const char *iwb200_job_last_error(const iwb200_job *job) { return job ? job->err.c_str() : "null job"; }
+
+void iwb200_job_destroy(iwb200_job *job) {
+  if (!job) return;
+  for (void *p : job->allocs) dev_free(p);
+  dev_free(job->d_in);
+  dev_free(job->d_out);
+  delete job;
+}
+
+// The context must have been through iwb_prepare() (iw_process_image does that; standalone callers use
+// iwb200_job_create which prepares a fresh context itself).
+static iwb200_job *job_build(iw_context *ctx, int device) {
+  iwb200_job *job = new iwb200_job();
+  job->ctx = ctx;
+  job->device = device;
+  if (!dev_select(device, job->err)) return job;
+
+  const int in_w = ctx->in_w, in_h = ctx->in_h;
+  const int out_w = ctx->img2.width, out_h = ctx->img2.height;
+  job->in_w = in_w;
+  job->in_h = in_h;
+  const bool transposed = (ctx->img1.orient_transform & 4) != 0;
+  job->phys_w = transposed ? ctx->img1.height : ctx->img1.width;
+  job->phys_h = transposed ? ctx->img1.width : ctx->img1.height;
+
+  const bool is_float_in = ctx->img1.sampletype == IW_SAMPLETYPE_FLOATINGPOINT;
+  if (is_float_in && ctx->img1.bit_depth != 32) { fail(job, "CUDA backend: floating-point input must be 32-bit"); return job; }
+  if (!is_float_in && ctx->img1.bit_depth != 1 && ctx->img1.bit_depth != 2 && ctx->img1.bit_depth != 4 &&
+      ctx->img1.bit_depth != 8 && ctx->img1.bit_depth != 16) {
+    fail(job, "CUDA backend: unsupported input bit depth");
+    return job;
+  }
+  if (is_float_in && !ctx->no_gamma && ctx->img1cs.cstype != IW_CSTYPE_LINEAR) {
+    // a continuous pow() cannot be tabulated; evaluating it on the device would not be bit-exact
+    fail(job, "CUDA backend: floating-point input is supported only in a linear colorspace");
+    return job;
+  }
+
+  DevInput &in = job->in;
+  in.pix = nullptr; in.bpr = ctx->img1.bpr; in.row_origin = 0;
+  in.width = ctx->img1.width; in.height = ctx->img1.height;
+  in.orient = (int)(ctx->img1.orient_transform & 7);
+  in.x0 = ctx->in_x0; in.y0 = ctx->in_y0;
+  in.depth = ctx->img1.bit_depth; in.nch_phys = ctx->in_nch_phys; in.is_float = is_float_in;
+
+  DevOutput &out = job->out;
+  out.pix = nullptr; out.row_origin = 0; out.width = out_w; out.height = out_h;
+  out.nch = ctx->out_nch; out.depth = ctx->img2.bit_depth;
+  out.is_float = ctx->img2.sampletype == IW_SAMPLETYPE_FLOATINGPOINT;
+  out.bpr = iw_calc_bytesperrow(out_w, ctx->img2.bit_depth * ctx->out_nch);
+
+  DevCommon &cm = job->cm;
+  cm.checker = ctx->bkgd_checkerboard; cm.check_size = ctx->check_size;
+  cm.check_ox = ctx->check_origin[IW_DIMENSION_H]; cm.check_oy = ctx->check_origin[IW_DIMENSION_V];
+  cm.bkgd1alpha = ctx->bkgd1alpha; cm.bkgd2alpha = ctx->bkgd2alpha; cm.intclamp = ctx->intclamp;
+
+  // processing order: alpha first (reference: src/imagew-main.c:1410-1435)
+  job->has_alpha = IW_IMGTYPE_HAS_ALPHA(ctx->mid_type);
+  job->nproc = 0;
+  if (job->has_alpha) job->mid_index[job->nproc++] = ctx->mid_alpha_index;
+  for (int m = 0; m < ctx->mid_nch; m++)
+    if (ctx->mid_ci[m].channeltype != IW_CHANNELTYPE_ALPHA) job->mid_index[job->nproc++] = m;
+
+  iw_csdescr lin_cs;
+  iw_make_linear_csdescr(&lin_cs);
+  const bool translucent = iwb_bkgd_is_translucent(ctx);
+  const bool nc_table_exists = !ctx->disable_out_tables && !ctx->no_gamma && ctx->img2cs.cstype != IW_CSTYPE_LINEAR &&
+                               !out.is_float && ctx->img2.bit_depth <= 8 && ((size_t)out_w) * out_h > 512;
+  const double *nc_dev = nullptr;
+  if (nc_table_exists) {  // midpoints between consecutive codes (reference: main.c:1197-1236)
+    std::vector<double> t(255);
+    double prev = 0.0;
+    for (int i = 0; i < 255; i++) {
+      double curr = iwb_to_linear(((double)(i + 1)) / 255, &ctx->img2cs);
+      t[i] = (prev + curr) / 2.0;
+      prev = curr;
+    }
+    nc_dev = job->upload(t.data(), t.size());
+    if (!nc_dev) return job;
+  }
+
+  std::vector<lut_key> luts;
+  double taps_v = 0, taps_h = 0;
+  for (int p = 0; p < job->nproc; p++) {
+    const int m = job->mid_index[p];
+    const iwb_mid_channel &mc = ctx->mid_ci[m];
+    const bool is_alpha = mc.channeltype == IW_CHANNELTYPE_ALPHA;
+    const iw_csdescr &cs_in = (is_alpha || ctx->no_gamma) ? lin_cs : ctx->img1cs;
+
+    // ---- input side
+    DevChanIn &ci = job->cin[p];
+    memset(&ci, 0, sizeof ci);
+    ci.in_ch = mc.in_channel; ci.to_gray = mc.to_gray; ci.gsf = ctx->grayscale_formula;
+    for (int k = 0; k < 3; k++) ci.gw[k] = ctx->gray_w[k];
+    const int nsrc = mc.to_gray ? 3 : 1;
+    for (int k = 0; k < nsrc; k++) {
+      int ch = mc.in_channel + k;
+      if (ch < ctx->in_nch_phys && !is_float_in) {
+        ci.lut[k] = input_lut(job, luts, ctx->img1.bit_depth, ctx->in_ci[ch].maxcode, cs_in);
+        if (!ci.lut[k]) return job;
+      }
+    }
+    ci.premult = mc.premultiplied;
+    ci.early_bkgd = !mc.premultiplied && ctx->apply_bkgd && ctx->bkgd_strategy == IWB_BKGD_EARLY;
+    ci.bkgd = mc.early_bkgd;
+    ci.alpha_ch = ctx->in_alpha_index;
+    if ((ci.premult || ci.early_bkgd) && ci.alpha_ch < ctx->in_nch_phys && !is_float_in) {
+      ci.alpha_lut = input_lut(job, luts, ctx->img1.bit_depth, ctx->in_ci[ci.alpha_ch].maxcode, lin_cs);
+      if (!ci.alpha_lut) return job;
+    }
+
+    // ---- resampling tables (shared between channels unless the plan says otherwise)
+    for (int d = 1; d >= 0; d--) {
+      std::vector<iwb_axis_table> &tabs = d == IW_DIMENSION_V ? job->vtab : job->htab;
+      DevAxis *dev = d == IW_DIMENSION_V ? job->vax : job->hax;
+      if (p > 0 && !ctx->axis[d].per_channel_tables) {
+        dev[p] = dev[0];
+        if (d == IW_DIMENSION_V) job->vtab_of[p] = 0;
+      } else {
+        tabs.emplace_back();
+        int n_in = d == IW_DIMENSION_V ? in_h : in_w;
+        int n_out = d == IW_DIMENSION_V ? out_h : out_w;
+        if (!iwb_build_axis_table(ctx, d, mc.channeltype, n_in, n_out, &tabs.back())) { fail(job, "weight table construction failed"); return job; }
+        if (!upload_axis(job, tabs.back(), &dev[p])) return job;
+        if (d == IW_DIMENSION_V) job->vtab_of[p] = (int)tabs.size() - 1;
+      }
+    }
+    {
+      const iwb_axis_table &vt = job->vtab[job->vtab_of[p]];
+      const iwb_axis_table &ht = ctx->axis[IW_DIMENSION_H].per_channel_tables ? job->htab.back() : job->htab[0];
+      taps_v += (vt.mode == 0 ? (double)vt.w.size() : (double)out_h) * in_w;
+      taps_h += (ht.mode == 0 ? (double)ht.w.size() : (double)out_w) * out_h;
+    }
+
+    // ---- output side
+    DevChanOut &o = job->cout[p];
+    memset(&o, 0, sizeof o);
+    o.out_ch = mc.out_channel;
+    o.is_alpha = is_alpha;
+    o.premult = mc.premultiplied;
+    o.late_bkgd = ctx->apply_bkgd && ctx->bkgd_strategy == IWB_BKGD_LATE;
+    o.bkgd_translucent = translucent;
+    o.maxcode = 255.0;
+    if (o.out_ch >= 0) {
+      const iwb_out_channel &oc = ctx->out_ci[o.out_ch];
+      const iw_csdescr &cs_out = (is_alpha || ctx->no_gamma) ? lin_cs : ctx->img2cs;
+      o.bkgd1 = oc.bkgd1; o.bkgd2 = oc.bkgd2;
+      o.maxcode = (double)oc.maxcode;
+      o.color_count = oc.color_count;
+      o.dfamily = oc.dither_family; o.dsubtype = oc.dither_subtype;
+      o.qmode = cs_out.cstype == IW_CSTYPE_LINEAR ? 0 : 1;
+      if (!out.is_float) {
+        o.use_nc = nc_table_exists && !is_alpha && o.dfamily == IW_DITHERFAMILY_NONE && o.color_count == 0;
+        o.nc_tbl = nc_dev;
+        if (o.qmode == 1 && !build_output_tables(job, ctx, oc, cs_out, &o)) return job;
+        o.errdiff = o.dfamily == IW_DITHERFAMILY_ERRDIFF;
+        if (o.errdiff) {
+          job->any_errdiff = 1;
+          memcpy(job->errdiff_m[p], kErrDiff[(o.dsubtype >= 0 && o.dsubtype <= 7) ? o.dsubtype : 0], sizeof kErrDiff[0]);
+        }
+        if (o.dfamily == IW_DITHERFAMILY_RANDOM) {
+          job->any_random = 1;
+          int seed = (o.dsubtype == IW_DITHERSUBTYPE_SAMEPATTERN && oc.channeltype != IW_CHANNELTYPE_ALPHA)
+                         ? ctx->random_seed : ctx->random_seed + oc.channeltype;
+          o.prng_t1 = iwb_prng_first_state(seed);
+        }
+      }
+    }
+  }
+
+  if (job->any_random) {
+    iwb_affine tbl[64];
+    iwb_prng_jump_table(tbl);
+    job->d_jump = (iwb_affine_t *)job->upload(tbl, 64);
+    if (!job->d_jump) return job;
+  }
+
+  job->negate = ctx->negate_target;
+  job->out_alpha_ch = IW_IMGTYPE_HAS_ALPHA(ctx->img2.imgtype) ? ctx->out_nch - 1 : -1;
+  // fully transparent pixels become black, unless reduced max codes are in use (reference: opt.c:1196-1200)
+  job->clear_transparent = !out.is_float && !ctx->reduced_out_maxcode && job->out_alpha_ch >= 0;
+
+  // chunk height: keep all FP32 intermediate planes of a chunk within ~48 MB so they live in L2
+  {
+    size_t per_row = (size_t)in_w * 4 * job->nproc;
+    size_t rows = per_row ? (size_t)(48u << 20) / per_row : 64;
+    rows = std::max<size_t>(rows, 16);
+    rows = std::min<size_t>(rows, (size_t)out_h);
+    job->chunk_rows = (int)rows;
+  }
+
+  iwb200_job_info &info = job->info;
+  info.out_width = out_w; info.out_height = out_h; info.out_imgtype = ctx->img2.imgtype;
+  info.out_bit_depth = ctx->img2.bit_depth; info.out_sampletype = ctx->img2.sampletype;
+  info.out_channels = ctx->out_nch; info.out_bpr = out.bpr;
+  info.in_width_phys = job->phys_w; info.in_height_phys = job->phys_h; info.in_bpr = ctx->img1.bpr;
+  info.bandable = !job->any_errdiff;
+  info.taps_v = taps_v; info.taps_h = taps_h;
+#if !defined(IWB_EMU)
+  const char *nofuse = iwb_option(ctx, "cuda:fused");
+  if (!(nofuse && !strcmp(nofuse, "0"))) fused_plan_build(job, &job->fused);
+  info.uses_fused_kernel = job->fused.enabled;
+#endif
+  return job;
+}
+
+static bool ensure_scratch(iwb200_job *job) {
+  if (job->inter[0]) return true;
+  const int W = job->out.width;
+  const size_t rows = job->chunk_rows;
+  for (int p = 0; p < job->nproc; p++) {
+    job->inter[p] = (float *)job->scratch(rows * job->in_w * sizeof(float));
+    if (!job->inter[p]) return false;
+    const DevChanOut &o = job->cout[p];
+    if (o.errdiff) {
+      job->lin_plane[p] = (double *)job->scratch(rows * W * sizeof(double));
+      job->errrows[p] = (double *)job->scratch((size_t)3 * W * sizeof(double));
+      if (!job->lin_plane[p] || !job->errrows[p]) return false;
+    }
+    if (o.dfamily == IW_DITHERFAMILY_RANDOM && o.out_ch >= 0 && !job->out.is_float) {
+      job->draws[p] = (uint32_t *)job->scratch(rows * W * sizeof(uint32_t));
+      if (!job->draws[p]) return false;
+    }
+  }
+  if (job->has_alpha) {
+    job->final_alpha = (float *)job->scratch(rows * W * sizeof(float));
+    if (!job->final_alpha) return false;
+  }
+  return true;
+}
+
+iwb200_job *iwb200_job_create(struct iw_context *ctx, int device) {
+  if (!ctx) return nullptr;
+  if (ctx->use_count == 0) {  // standalone use: decide the plan now; the context is consumed like in iw_process_image
+    ctx->use_count++;
+    if (!iwb_prepare(ctx)) return nullptr;
+  }
+  iwb200_job *job = job_build(ctx, device);
+  if (!job->err.empty()) {
+    iw_set_errorf(ctx, "%s", job->err.c_str());
+    iwb200_job_destroy(job);
+    return nullptr;
+  }
+  return job;
+}
+
+int iwb200_job_get_info(const iwb200_job *job, struct iwb200_job_info *info) {
+  if (!job || !info) return 0;
+  *info = job->info;
+  return 1;
+}
+
+int iwb200_job_band_input_rows(const iwb200_job *job, int r0, int r1, int *first, int *last) {
+  if (!job || r0 < 0 || r1 > job->out.height || r0 >= r1) return 0;
+  if (job->in.orient & 4) {  // transposed storage: an output band touches every stored row
+    *first = 0; *last = job->phys_h - 1;
+    return 1;
+  }
+  int lo = job->in_h, hi = -1;
+  for (const iwb_axis_table &t : job->vtab) {
+    lo = std::min(lo, t.min_src(r0, r1));
+    hi = std::max(hi, t.max_src(r0, r1));
+  }
+  if (hi < lo) { lo = 0; hi = 0; }
+  int a = job->in.y0 + lo, b = job->in.y0 + hi;  // logical rows
+  if (job->in.orient & 2) { int t = a; a = job->in.height - 1 - b; b = job->in.height - 1 - t; }
+  *first = a; *last = b;
+  return 1;
+}
+
+int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int in_row_origin, void *d_out,
+                          size_t out_bpr, int r0, int r1, void *stream_) {
+  if (!job) return 0;
+  iwb_stream stream = (iwb_stream)stream_;
+  if (r0 < 0 || r1 > job->out.height || r0 >= r1) return fail(job, "invalid output row band");
+  if (job->any_errdiff && r0 != job->errdiff_next_row && r0 != 0)
+    return fail(job, "error-diffusion dither must be processed in row order from row 0");
+#if !defined(IWB_EMU)
+  cudaSetDevice(job->device);
+#endif
+  DevInput in = job->in;
+  in.pix = (const uint8_t *)d_in; in.bpr = in_bpr; in.row_origin = in_row_origin;
+  DevOutput out = job->out;
+  out.pix = (uint8_t *)d_out; out.bpr = out_bpr; out.row_origin = r0;
+
+#if !defined(IWB_EMU)
+  if (job->fused.enabled) {
+    if (!fused_run(job, &job->fused, in, out, r0, r1, stream)) return 0;
+    return 1;
+  }
+#endif
+  if (!ensure_scratch(job)) return 0;
+  const int W = out.width;
+  if (job->any_errdiff && r0 == 0)
+    for (int p = 0; p < job->nproc; p++)
+      if (job->errrows[p]) dev_zero(job->errrows[p], (size_t)3 * W * sizeof(double), stream);
+
+  for (int c0 = r0; c0 < r1; c0 += job->chunk_rows) {
+    const int c1 = std::min(r1, c0 + job->chunk_rows);
+    const size_t rows = c1 - c0;
+    // vertical pass, all channels
+    VPassParams vp;
+    vp.in = in; vp.cm = job->cm; vp.nch = job->nproc; vp.in_w = job->in_w; vp.row0 = c0; vp.row1 = c1;
+    for (int p = 0; p < job->nproc; p++) { vp.ch[p] = job->cin[p]; vp.ax[p] = job->vax[p]; vp.inter[p] = job->inter[p]; }
+    launch<VPassBody>(vp, (size_t)job->nproc * rows * job->in_w, stream);
+
+    if (job->any_random) {
+      PrngParams pp;
+      pp.nch = 0; pp.W = W; pp.row0 = c0; pp.rows = (int)rows; pp.seg = 64; pp.segs_per_row = (W + 63) / 64; pp.jump = job->d_jump;
+      for (int p = 0; p < job->nproc; p++)
+        if (job->draws[p]) { pp.t1[pp.nch] = job->cout[p].prng_t1; pp.draws[pp.nch] = job->draws[p]; pp.nch++; }
+      launch<PrngBody>(pp, (size_t)pp.nch * rows * pp.segs_per_row, stream);
+    }
+
+    // horizontal pass + epilogue: alpha alone first, then every colour channel
+    for (int pass = 0; pass < 2; pass++) {
+      HPassParams hp;
+      hp.cm = job->cm; hp.out = out; hp.in_w = job->in_w; hp.row0 = c0; hp.row1 = c1; hp.inter_row0 = c0;
+      hp.final_alpha = job->final_alpha; hp.alpha_row0 = c0; hp.nch = 0;
+      int lo = pass == 0 ? 0 : (job->has_alpha ? 1 : 0);
+      int hi = pass == 0 ? (job->has_alpha ? 1 : 0) : job->nproc;
+      for (int p = lo; p < hi; p++) {
+        int k = hp.nch++;
+        hp.ch[k] = job->cout[p]; hp.ax[k] = job->hax[p]; hp.inter[k] = job->inter[p];
+        hp.lin_plane[k] = job->lin_plane[p]; hp.draws[k] = job->draws[p];
+      }
+      launch<HPassBody>(hp, (size_t)hp.nch * rows * W, stream);
+    }
+
+    if (job->any_errdiff) {
+      ErrDiffParams ep;
+      ep.out = out; ep.nch = 0; ep.row0 = c0; ep.row1 = c1;
+      for (int p = 0; p < job->nproc; p++)
+        if (job->cout[p].errdiff) {
+          int k = ep.nch++;
+          ep.ch[k] = job->cout[p]; ep.lin_plane[k] = job->lin_plane[p]; ep.err[k] = job->errrows[p];
+          memcpy(ep.m[k], job->errdiff_m[p], sizeof ep.m[k]);
+        }
+      launch_serial<ErrDiffBody>(ep, ep.nch, stream);
+      job->errdiff_next_row = c1;
+    }
+
+    if (job->negate || job->clear_transparent) {
+      PostParams pp;
+      pp.out = out; pp.row0 = c0; pp.row1 = c1; pp.negate = job->negate; pp.alpha_ch = job->out_alpha_ch;
+      pp.clear_transparent = job->clear_transparent;
+      for (int c = 0; c < 4; c++) pp.maxcode[c] = c < job->ctx->out_nch ? job->ctx->out_ci[c].maxcode : 0;
+      launch<PostBody>(pp, rows * W, stream);
+    }
+  }
+#if !defined(IWB_EMU)
+  if (cudaGetLastError() != cudaSuccess) return fail(job, "kernel launch failed");
+#endif
+  return 1;
+}
+
+int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *h_out, size_t out_bpr, int r0,
+                        int r1) {
+  if (!job) return 0;
+  int first, last;
+  if (!iwb200_job_band_input_rows(job, r0, r1, &first, &last)) return fail(job, "invalid output row band");
+  first = std::max(first, 0);
+  last = std::min(last, job->phys_h - 1);
+  const size_t in_bytes = (size_t)(last - first + 1) * in_bpr;
+  const size_t out_bytes = (size_t)(r1 - r0) * out_bpr;
+  if (job->d_in_bytes < in_bytes) { dev_free(job->d_in); job->d_in = dev_alloc(in_bytes, job->err); job->d_in_bytes = in_bytes; }
+  if (job->d_out_bytes < out_bytes) { dev_free(job->d_out); job->d_out = dev_alloc(out_bytes, job->err); job->d_out_bytes = out_bytes; }
+  if (!job->d_in || !job->d_out) { job->d_in_bytes = job->d_out_bytes = 0; return 0; }
+  iwb_timings &tm = job->ctx->timings;
+#if !defined(IWB_EMU)
+  cudaEvent_t e[4];
+  for (auto &x : e) cudaEventCreate(&x);
+  cudaEventRecord(e[0], 0);
+#endif
+  if (!dev_h2d(job->d_in, (const uint8_t *)h_in + (size_t)first * in_bpr, in_bytes, 0, job->err)) return 0;
+#if !defined(IWB_EMU)
+  cudaEventRecord(e[1], 0);
+#endif
+  if (!iwb200_job_run_device(job, job->d_in, in_bpr, first, job->d_out, out_bpr, r0, r1, 0)) return 0;
+#if !defined(IWB_EMU)
+  cudaEventRecord(e[2], 0);
+#endif
+  if (!dev_d2h(h_out, job->d_out, out_bytes, 0, job->err)) return 0;
+#if !defined(IWB_EMU)
+  cudaEventRecord(e[3], 0);
+#endif
+  if (!dev_sync(0, job->err)) return 0;
+#if !defined(IWB_EMU)
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e[0], e[1]); tm.h2d_ms = ms;
+  cudaEventElapsedTime(&ms, e[1], e[2]); tm.kernel_ms = ms;
+  cudaEventElapsedTime(&ms, e[2], e[3]); tm.d2h_ms = ms;
+  for (auto &x : e) cudaEventDestroy(x);
+#else
+  (void)tm;
+#endif
+  return 1;
+}
+
+}  // extern "C"
