@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- output Mpix/s of the pixel pipeline on BASELINE.json's headline configuration (cfg2:
+7680x4320 RGB8 -> 3840x2160, Lanczos3 in linear light, ordered dither, 8-bit sRGB out).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2] [--impl ours|reference]
+
+A step = one pass of the whole pipeline over one synthetic image.  `value` times the step with the image already
+resident in HBM (CUDA events on the launching stream, rotating input/output buffers larger than L2 between
+steps); `e2e` times the public C-ABI call iw_process_image() on HOST buffers, so it contains the H2D copy of the
+input and the D2H copy of the result.  With N > 1 (launched by torchrun, one rank per GPU) every rank processes its
+own image (images shard across GPUs with no data-path collective: weak scaling); the time is the max over ranks.
+`--impl reference` times the unmodified reference build (oracle/_ref) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from imageworsener_b200 import configs, libimagew as L  # noqa: E402
+
+METRIC = "output Mpix/s, 8K->4K Lanczos3 linear-light RGB8 + ordered dither"
+KERNEL_CLASSES = ["v_pass", "h_pass_epilogue", "prng_fill", "errdiff", "post", "fused_vh_tile"]
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while a timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_ctx(lib: L.Lib, cfg, rows=None, options=None):
+    ctx = lib.iw_create_context(None)
+    if cfg.max_malloc:
+        lib.iw_set_max_malloc(ctx, cfg.max_malloc)
+    if rows is not None:
+        lib.set_input_from_numpy(ctx, rows, cfg.imgtype, cfg.bit_depth, cfg.in_w, cfg.in_h)
+    else:  # header only: pixels live in HBM
+        img = L.iw_image()
+        img.imgtype, img.bit_depth, img.sampletype = cfg.imgtype, cfg.bit_depth, 0
+        img.width, img.height, img.bpr, img.pixels = cfg.in_w, cfg.in_h, cfg.in_bpr, None
+        lib.iw_set_input_image(ctx, C.byref(img))
+    for k, v in (options or {}).items():
+        lib.iw_set_option(ctx, k.encode(), str(v).encode())
+    cfg.apply(lib, ctx)
+    return ctx
+
+
+def cpu_reference_once(cfg, rows, threads: int):
+    """`threads` reference contexts in parallel, one image each (the reference has no intra-image threading).
+    Returns seconds."""
+    ref = L.load_reference()
+    errs = []
+
+    def work():
+        try:
+            configs.run_host(ref, cfg, rows)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work) for _ in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    if errs:
+        raise errs[0]
+    return dt
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 16))
+    total = args.steps + args.warmup
+    scale = 1 if total <= 4 else (2 if total <= 12 else 4)   # bound the run to a few minutes
+    cfg = configs.get(args.config, scale=scale)
+    helper = L.load_product()            # only the synthetic-input helper (plain host C) is used from it
+    rows = configs.synth_rows(helper, cfg)
+    for _ in range(args.warmup):
+        cpu_reference_once(cfg, rows, threads)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_reference_once(cfg, rows, threads)
+    value = threads * args.steps * cfg.out_mpix / t
+    sample = (f"{threads} reference contexts in parallel (one thread each), each resizing one "
+              f"{cfg.in_w}x{cfg.in_h} image (1/{scale} linear scale of the workload) per step")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {cfg.description}", "in": [cfg.in_w, cfg.in_h],
+                       "out": [cfg.out_w, cfg.out_h]},
+            "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": threads, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    lib = L.load_product()
+    dll = lib.dll
+    dll.iwb200_kernel_launch_count.restype = C.c_ulonglong
+    dll.iwb200_job_create.restype = C.c_void_p
+    dll.iwb200_job_create.argtypes = [C.c_void_p, C.c_int]
+    dll.iwb200_job_destroy.argtypes = [C.c_void_p]
+    dll.iwb200_job_run_device.restype = C.c_int
+    dll.iwb200_job_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
+                                          C.c_int, C.c_int, C.c_void_p]
+    dll.iwb200_job_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    dll.iwb200_job_reset_stats.argtypes = [C.c_void_p]
+    dll.iwb200_job_kernel_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    dll.iwb200_job_last_error.restype = C.c_char_p
+    dll.iwb200_job_last_error.argtypes = [C.c_void_p]
+
+    class Info(C.Structure):
+        _fields_ = [("out_width", C.c_int), ("out_height", C.c_int), ("out_imgtype", C.c_int),
+                    ("out_bit_depth", C.c_int), ("out_sampletype", C.c_int), ("out_channels", C.c_int),
+                    ("out_bpr", C.c_size_t), ("in_width_phys", C.c_int), ("in_height_phys", C.c_int),
+                    ("in_bpr", C.c_size_t), ("bandable", C.c_int), ("uses_fused_kernel", C.c_int),
+                    ("taps_v", C.c_double), ("taps_h", C.c_double)]
+    dll.iwb200_job_get_info.argtypes = [C.c_void_p, C.POINTER(Info)]
+
+    cfg = configs.get(args.config)
+    rows = configs.synth_rows(lib, cfg, seed=configs.XORSHIFT_SEED + rank)
+
+    # ---------------- device-resident throughput -------------------------------------------------------
+    ctx = make_ctx(lib, cfg, rows=None, options={"cuda:device": local_rank})
+    job = dll.iwb200_job_create(ctx, local_rank)
+    if not job:
+        raise SystemExit("job creation failed: " + lib.errmsg(ctx))
+    info = Info()
+    dll.iwb200_job_get_info(job, C.byref(info))
+    out_bytes = info.out_bpr * info.out_height
+    nbuf = max(2, int(np.ceil(300e6 / (cfg.in_bytes + out_bytes))) + 1)   # rotate through > 2x L2 of data
+    nbuf = min(nbuf, 8)
+    host = torch.from_numpy(rows.reshape(-1))
+    d_in = []
+    for b in range(nbuf):
+        t = host.to("cuda", non_blocking=False)
+        if b:
+            t = torch.roll(t, shifts=b * 4099)       # different bytes per buffer, same statistics
+        d_in.append(t.contiguous())
+    d_out = [torch.empty(out_bytes, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
+    stream = torch.cuda.Stream()
+
+    def step(i):
+        ok = dll.iwb200_job_run_device(job, d_in[i % nbuf].data_ptr(), cfg.in_bpr, 0, d_out[i % nbuf].data_ptr(),
+                                       info.out_bpr, 0, info.out_height, stream.cuda_stream)
+        if not ok:
+            raise SystemExit("run_device failed: " + dll.iwb200_job_last_error(job).decode())
+
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = dll.iwb200_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for i in range(args.steps):
+            step(i)
+        e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = dll.iwb200_kernel_launch_count() - l0
+    # keep the sampler running a little longer if the region was very short, so it sees load
+    if ms_total < 1500:
+        with torch.cuda.stream(stream):
+            t_end = time.time() + 1.5
+            i = 0
+            while time.time() < t_end:
+                step(i)
+                i += 1
+                if i % 8 == 0:
+                    stream.synchronize()
+        stream.synchronize()
+    clocks = sampler.stop()
+    ms_per_step = ms_total / args.steps
+    value = world * cfg.out_mpix / (ms_per_step / 1000.0)
+
+    # ---------------- per-kernel device time -> roofline of the dominant kernel ------------------------
+    dll.iwb200_job_set_profiling(job, 1)
+    dll.iwb200_job_reset_stats(job)
+    prof_steps = min(5, args.steps)
+    with torch.cuda.stream(stream):
+        for i in range(prof_steps):
+            step(i)
+    stream.synchronize()
+    stats = {}
+    for k, nm in enumerate(KERNEL_CLASSES):
+        n, ms = C.c_int(0), C.c_double(0.0)
+        dll.iwb200_job_kernel_stats(job, k, C.byref(n), C.byref(ms))
+        if n.value:
+            stats[nm] = {"launches_per_step": n.value / prof_steps, "ms_per_step": ms.value / prof_steps}
+    dll.iwb200_job_set_profiling(job, 0)
+    dom = max(stats, key=lambda k: stats[k]["ms_per_step"])
+    alg_bytes_step = cfg.in_bytes + out_bytes                        # read input once + write output once
+    lp = stats[dom]["launches_per_step"]
+    avg_launch_ms = stats[dom]["ms_per_step"] / lp
+    achieved = (alg_bytes_step / lp) / (avg_launch_ms * 1e-3) / 1e9   # GB/s, algorithmic bytes of the rows a launch covers
+    peak, peak_src = measured_peak_hbm()
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_step": alg_bytes_step, "launches_per_step": lp,
+                "avg_launch_ms": avg_launch_ms, "kernel_ms_per_step": stats,
+                "fp64_tap_pairs_per_step": info.taps_v + info.taps_h,
+                "note": "FP64 issue (DMUL+DADD per tap, FMA forbidden by bit-exactness) binds before HBM; see DESIGN.md"}
+    dll.iwb200_job_destroy(job)
+    lib.iw_destroy_context(ctx)
+
+    # ---------------- end to end through iw_process_image on host buffers ------------------------------
+    def e2e_once():
+        c = make_ctx(lib, cfg, rows=rows, options={"cuda:device": local_rank})
+        t0 = time.perf_counter()
+        ok = lib.iw_process_image(c)
+        dt = time.perf_counter() - t0
+        if not ok:
+            raise SystemExit("iw_process_image failed: " + lib.errmsg(c))
+        img = L.iw_image()
+        lib.iw_get_output_image(c, C.byref(img))
+        first = C.cast(img.pixels, C.POINTER(C.c_uint8))[0]     # the result is host-resident
+        lib.iw_destroy_context(c)
+        return dt, first
+
+    for _ in range(2):
+        e2e_once()
+    barrier()
+    e2e_t = 0.0
+    for _ in range(args.e2e_steps):
+        dt, _ = e2e_once()
+        e2e_t += dt
+    barrier()
+    e2e_ms = max_over_ranks(1000.0 * e2e_t / args.e2e_steps)
+    e2e = {"value": world * cfg.out_mpix / (e2e_ms / 1000.0), "unit": "Mpix/s", "h2d_bytes_per_step": cfg.in_bytes,
+           "d2h_bytes_per_step": out_bytes, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
+           "api": "iw_process_image (host buffers; plan + H2D + kernels + D2H inside the timed call)"}
+
+    # ---------------- CPU baseline: the reference build on this box's host cores ------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(L.REFERENCE_SO):
+        dt = cpu_reference_once(cfg, rows, 1)
+        cpu = {"value": cfg.out_mpix / dt, "unit": "Mpix/s", "cores": 1, "kind": "reference",
+               "sample": f"one full {cfg.in_w}x{cfg.in_h} image through the unmodified reference build, 1 thread "
+                         f"(it has no intra-image threading), {dt:.1f} s", "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{args.config}: {cfg.description}", "in": [cfg.in_w, cfg.in_h],
+                           "out": [cfg.out_w, cfg.out_h], "images_per_step_per_gpu": 1,
+                           "sharding": "one image per GPU, no data-path collective" if world > 1 else "single GPU",
+                           "l2_defeat": f"{nbuf} rotating input/output buffer sets ({nbuf * (cfg.in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2)",
+                           "fused_kernel": bool(info.uses_fused_kernel)},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

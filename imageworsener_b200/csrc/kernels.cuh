@@ -2,7 +2,7 @@
 //
 // Parity rules that shape this file:
 //   * every tap is  acc = acc + in*w  in list order, FP64, multiply and add rounded SEPARATELY (the reference
-//     x86-64 build has no FMA): all parity-critical arithmetic goes through dmul/dadd/dsub/ddiv, which map to
+//     x86-64 build has no FMA): all parity-critical arithmetic goes through xmul/xadd/xsub/xdiv, which map to
 //     __dmul_rn/__dadd_rn/... on the device so no flag or optimiser can contract them;
 //   * the vertical pass runs first and its result is rounded to float; the resized alpha plane is rounded to
 //     float before it un-premultiplies colour (reference: src/imagew-main.c:905-912, :1057-1061, :1093);
@@ -26,28 +26,28 @@
 #endif
 
 // ---- rounding-exact primitives ------------------------------------------------------------------------
-IWB_HD double dmul(double a, double b) {
+IWB_HD double xmul(double a, double b) {
 #if defined(__CUDA_ARCH__)
   return __dmul_rn(a, b);
 #else
   return a * b;
 #endif
 }
-IWB_HD double dadd(double a, double b) {
+IWB_HD double xadd(double a, double b) {
 #if defined(__CUDA_ARCH__)
   return __dadd_rn(a, b);
 #else
   return a + b;
 #endif
 }
-IWB_HD double dsub(double a, double b) {
+IWB_HD double xsub(double a, double b) {
 #if defined(__CUDA_ARCH__)
   return __dsub_rn(a, b);
 #else
   return a - b;
 #endif
 }
-IWB_HD double ddiv(double a, double b) {
+IWB_HD double xdiv(double a, double b) {
 #if defined(__CUDA_ARCH__)
   return __ddiv_rn(a, b);
 #else
@@ -186,7 +186,7 @@ IWB_HD double gray_of(const DevChanIn &ci, double r, double g, double b) {
   } else if (ci.gsf != 2) {
     return 0.0;
   }
-  return dadd(dadd(dmul(ci.gw[0], r), dmul(ci.gw[1], g)), dmul(ci.gw[2], b));
+  return xadd(xadd(xmul(ci.gw[0], r), xmul(ci.gw[1], g)), xmul(ci.gw[2], b));
 }
 
 // Linear sample of intermediate channel `ci` at logical (x,y), with premultiply / early background
@@ -206,8 +206,8 @@ IWB_HD double fetch_linear(const DevInput &in, const DevChanIn &ci, int x, int y
     if (ci.alpha_ch >= in.nch_phys) a = 1.0;
     else if (in.is_float) a = raw_float(in, px, py, ci.alpha_ch);
     else a = ci.alpha_lut[raw_code(in, px, py, ci.alpha_ch)];
-    if (ci.premult) v = dmul(v, a);
-    else v = dadd(dmul(a, v), dmul(dsub(1.0, a), ci.bkgd));
+    if (ci.premult) v = xmul(v, a);
+    else v = xadd(xmul(a, v), xmul(xsub(1.0, a), ci.bkgd));
   }
   return v;
 }
@@ -246,7 +246,7 @@ struct VPassBody {
       for (int t = ax.first[j]; t < t1; t++) {
         int s = ax.src[t];
         double v = s >= 0 ? fetch_linear(p.in, ci, i, s) : ax.edge_value;
-        acc = dadd(acc, dmul(v, ax.w[t]));
+        acc = xadd(acc, xmul(v, ax.w[t]));
       }
     }
     if (p.cm.intclamp) acc = acc < 0.0 ? 0.0 : (acc > 1.0 ? 1.0 : acc);
@@ -265,24 +265,24 @@ IWB_HD Candidates candidates_linear(const DevChanOut &o, double s) {
   Candidates c;
   double cvt = s > 0.999999999 ? 1.0 : s;
   if (o.color_count == 0) {
-    double e = dmul(cvt, o.maxcode);
+    double e = xmul(cvt, o.maxcode);
     if (e > o.maxcode) e = o.maxcode;
     if (e < 0.0) e = 0.0;
     c.code_lo = floor(e);
     c.code_hi = ceil(e);
   } else {
     double pm = (double)(o.color_count - 1);
-    double e = dmul(cvt, pm);
+    double e = xmul(cvt, pm);
     if (e > pm) e = pm;
     if (e < 0.0) e = 0.0;
-    double step = ddiv(o.maxcode, pm);
-    c.code_lo = floor(dadd(0.5000000001, dmul(floor(e), step)));
-    c.code_hi = floor(dadd(0.5000000001, dmul(ceil(e), step)));
+    double step = xdiv(o.maxcode, pm);
+    c.code_lo = floor(xadd(0.5000000001, xmul(floor(e), step)));
+    c.code_hi = floor(xadd(0.5000000001, xmul(ceil(e), step)));
   }
   unsigned lo = (unsigned)c.code_lo, hi = (unsigned)c.code_hi;
   c.exact = lo == hi;
-  c.lin_lo = ddiv((double)lo, o.maxcode);
-  c.lin_hi = ddiv((double)hi, o.maxcode);
+  c.lin_lo = xdiv((double)lo, o.maxcode);
+  c.lin_hi = xdiv((double)hi, o.maxcode);
   return c;
 }
 
@@ -368,14 +368,14 @@ IWB_HD double composite(const DevCommon &cm, const DevChanOut &o, double s, cons
   if (o.bkgd_translucent) ba = alt ? cm.bkgd2alpha : cm.bkgd1alpha;
   if (o.premult) {
     double a = (double)final_alpha[(size_t)y * out_w + x];
-    if (a != 0.0) s = ddiv(s, a);
+    if (a != 0.0) s = xdiv(s, a);
     if (o.late_bkgd) {
       double bk = alt ? o.bkgd2 : o.bkgd1;
-      if (o.bkgd_translucent) s = dadd(dmul(s, a), dmul(dmul(bk, ba), dsub(1.0, a)));
-      else s = dadd(dmul(s, a), dmul(bk, dsub(1.0, a)));
+      if (o.bkgd_translucent) s = xadd(xmul(s, a), xmul(xmul(bk, ba), xsub(1.0, a)));
+      else s = xadd(xmul(s, a), xmul(bk, xsub(1.0, a)));
     }
   } else if (o.is_alpha && o.bkgd_translucent) {
-    s = dadd(s, dmul(ba, dsub(1.0, s)));
+    s = xadd(s, xmul(ba, xsub(1.0, s)));
   }
   return s;
 }
@@ -387,15 +387,15 @@ IWB_HD double quantise(const DevChanOut &o, double s, int x, int y, uint32_t dra
   if (o.use_nc) return nearest_by_midpoints(o.nc_tbl, s);
   Candidates c = o.qmode == 0 ? candidates_linear(o, s) : candidates_table(o, s);
   if (c.exact) return c.code_lo;
-  double d_floor = dsub(s, c.lin_lo), d_ceil = dsub(c.lin_hi, s);
+  double d_floor = xsub(s, c.lin_lo), d_ceil = xsub(c.lin_hi, s);
   if (o.dfamily == 0) return d_ceil <= d_floor ? c.code_hi : c.code_lo;
   if (o.dfamily == 1) {
-    double frac = ddiv(d_floor, dadd(d_floor, d_ceil));
+    double frac = xdiv(d_floor, xadd(d_floor, d_ceil));
     return frac >= ordered_threshold(o.dsubtype, x, y) ? c.code_hi : c.code_lo;
   }
   if (o.dfamily == 3) {
-    double frac = ddiv(d_floor, dadd(d_floor, d_ceil));
-    double thr = ddiv((double)draw, (double)0xffffffffu);
+    double frac = xdiv(d_floor, xadd(d_floor, d_ceil));
+    double thr = xdiv((double)draw, (double)0xffffffffu);
     return frac >= thr ? c.code_hi : c.code_lo;
   }
   return 0.0;  // unsupported dither family: the reference stores 0 as well
@@ -440,7 +440,7 @@ struct HPassBody {
       for (int t = ax.first[x]; t < t1; t++) {
         int s = ax.src[t];
         double v = s >= 0 ? (double)row[s] : ax.edge_value;
-        acc = dadd(acc, dmul(v, ax.w[t]));
+        acc = xadd(acc, xmul(v, ax.w[t]));
       }
     }
     if (p.cm.intclamp) acc = acc < 0.0 ? 0.0 : (acc > 1.0 ? 1.0 : acc);
@@ -512,36 +512,36 @@ struct ErrDiffBody {
       for (int z = 0; z < W; z++) {
         const int x = (y % 2) ? W - 1 - z : z;
         double s = clamp01(src[x]);
-        s = dadd(s, e0[x]);
+        s = xadd(s, e0[x]);
         if (s > 1.0) s = 1.0; else if (s < 0.0) s = 0.0;
         Candidates k = o.qmode == 0 ? candidates_linear(o, s) : candidates_table(o, s);
         double code;
         if (k.exact) {
           code = k.code_lo;
         } else {
-          double d_floor = dsub(s, k.lin_lo), d_ceil = dsub(k.lin_hi, s);
+          double d_floor = xsub(s, k.lin_lo), d_ceil = xsub(k.lin_hi, s);
           double err;
           if (d_ceil <= d_floor) { err = -d_ceil; code = k.code_hi; }
           else { err = d_floor; code = k.code_lo; }
           // distribute (src/imagew-main.c:545-566)
           if ((x - fwd) >= 0 && (x - fwd) < W) {
             if ((x - 2 * fwd) >= 0 && (x - 2 * fwd) < W) {
-              e1[x - 2 * fwd] = dadd(e1[x - 2 * fwd], dmul(err, m[2]));
-              e2[x - 2 * fwd] = dadd(e2[x - 2 * fwd], dmul(err, m[7]));
+              e1[x - 2 * fwd] = xadd(e1[x - 2 * fwd], xmul(err, m[2]));
+              e2[x - 2 * fwd] = xadd(e2[x - 2 * fwd], xmul(err, m[7]));
             }
-            e1[x - fwd] = dadd(e1[x - fwd], dmul(err, m[3]));
-            e2[x - fwd] = dadd(e2[x - fwd], dmul(err, m[8]));
+            e1[x - fwd] = xadd(e1[x - fwd], xmul(err, m[3]));
+            e2[x - fwd] = xadd(e2[x - fwd], xmul(err, m[8]));
           }
-          e1[x] = dadd(e1[x], dmul(err, m[4]));
-          e2[x] = dadd(e2[x], dmul(err, m[9]));
+          e1[x] = xadd(e1[x], xmul(err, m[4]));
+          e2[x] = xadd(e2[x], xmul(err, m[9]));
           if ((x + fwd) >= 0 && (x + fwd) < W) {
-            e0[x + fwd] = dadd(e0[x + fwd], dmul(err, m[0]));
-            e1[x + fwd] = dadd(e1[x + fwd], dmul(err, m[5]));
-            e2[x + fwd] = dadd(e2[x + fwd], dmul(err, m[10]));
+            e0[x + fwd] = xadd(e0[x + fwd], xmul(err, m[0]));
+            e1[x + fwd] = xadd(e1[x + fwd], xmul(err, m[5]));
+            e2[x + fwd] = xadd(e2[x + fwd], xmul(err, m[10]));
             if ((x + 2 * fwd) >= 0 && (x + 2 * fwd) < W) {
-              e0[x + 2 * fwd] = dadd(e0[x + 2 * fwd], dmul(err, m[1]));
-              e1[x + 2 * fwd] = dadd(e1[x + 2 * fwd], dmul(err, m[6]));
-              e2[x + 2 * fwd] = dadd(e2[x + 2 * fwd], dmul(err, m[11]));
+              e0[x + 2 * fwd] = xadd(e0[x + 2 * fwd], xmul(err, m[1]));
+              e1[x + 2 * fwd] = xadd(e1[x + 2 * fwd], xmul(err, m[6]));
+              e2[x + 2 * fwd] = xadd(e2[x + 2 * fwd], xmul(err, m[11]));
             }
           }
         }

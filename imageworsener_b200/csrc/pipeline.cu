@@ -130,6 +130,12 @@ struct iwb200_job {
   uint32_t *draws[4] = {nullptr, nullptr, nullptr, nullptr};
   double *errrows[4] = {nullptr, nullptr, nullptr, nullptr};
   int errdiff_next_row = 0;
+  // optional per-kernel event timing
+  int profiling = 0;
+  struct timed { int which; void *a, *b; };
+  std::vector<timed> pending;
+  int stat_n[6] = {0, 0, 0, 0, 0, 0};
+  double stat_ms[6] = {0, 0, 0, 0, 0, 0};
   // staging for run_host
   void *d_in = nullptr; size_t d_in_bytes = 0;
   void *d_out = nullptr; size_t d_out_bytes = 0;
@@ -158,6 +164,21 @@ bool fail(iwb200_job *job, const std::string &m) {
   if (job->err.empty()) job->err = m;
   return false;
 }
+
+// Bracket one launch with events when profiling is on.
+struct prof_scope {
+  iwb200_job *job; int which; iwb_stream s; void *a = nullptr;
+  prof_scope(iwb200_job *j, int w, iwb_stream st) : job(j), which(w), s(st) {
+#if !defined(IWB_EMU)
+    if (job->profiling) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); a = e; }
+#endif
+  }
+  ~prof_scope() {
+#if !defined(IWB_EMU)
+    if (job->profiling && a) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); job->pending.push_back({which, a, (void *)e}); }
+#endif
+  }
+};
 
 bool upload_axis(iwb200_job *job, const iwb_axis_table &t, DevAxis *d) {
   d->mode = t.mode;
@@ -551,14 +572,14 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
     VPassParams vp;
     vp.in = in; vp.cm = job->cm; vp.nch = job->nproc; vp.in_w = job->in_w; vp.row0 = c0; vp.row1 = c1;
     for (int p = 0; p < job->nproc; p++) { vp.ch[p] = job->cin[p]; vp.ax[p] = job->vax[p]; vp.inter[p] = job->inter[p]; }
-    launch<VPassBody>(vp, (size_t)job->nproc * rows * job->in_w, stream);
+    { prof_scope ps(job, 0, stream); launch<VPassBody>(vp, (size_t)job->nproc * rows * job->in_w, stream); }
 
     if (job->any_random) {
       PrngParams pp;
       pp.nch = 0; pp.W = W; pp.row0 = c0; pp.rows = (int)rows; pp.seg = 64; pp.segs_per_row = (W + 63) / 64; pp.jump = job->d_jump;
       for (int p = 0; p < job->nproc; p++)
         if (job->draws[p]) { pp.t1[pp.nch] = job->cout[p].prng_t1; pp.draws[pp.nch] = job->draws[p]; pp.nch++; }
-      launch<PrngBody>(pp, (size_t)pp.nch * rows * pp.segs_per_row, stream);
+      { prof_scope ps(job, 2, stream); launch<PrngBody>(pp, (size_t)pp.nch * rows * pp.segs_per_row, stream); }
     }
 
     // horizontal pass + epilogue: alpha alone first, then every colour channel
@@ -573,7 +594,7 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
         hp.ch[k] = job->cout[p]; hp.ax[k] = job->hax[p]; hp.inter[k] = job->inter[p];
         hp.lin_plane[k] = job->lin_plane[p]; hp.draws[k] = job->draws[p];
       }
-      launch<HPassBody>(hp, (size_t)hp.nch * rows * W, stream);
+      { prof_scope ps(job, 1, stream); launch<HPassBody>(hp, (size_t)hp.nch * rows * W, stream); }
     }
 
     if (job->any_errdiff) {
@@ -585,7 +606,7 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
           ep.ch[k] = job->cout[p]; ep.lin_plane[k] = job->lin_plane[p]; ep.err[k] = job->errrows[p];
           memcpy(ep.m[k], job->errdiff_m[p], sizeof ep.m[k]);
         }
-      launch_serial<ErrDiffBody>(ep, ep.nch, stream);
+      { prof_scope ps(job, 3, stream); launch_serial<ErrDiffBody>(ep, ep.nch, stream); }
       job->errdiff_next_row = c1;
     }
 
@@ -594,13 +615,50 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
       pp.out = out; pp.row0 = c0; pp.row1 = c1; pp.negate = job->negate; pp.alpha_ch = job->out_alpha_ch;
       pp.clear_transparent = job->clear_transparent;
       for (int c = 0; c < 4; c++) pp.maxcode[c] = c < job->ctx->out_nch ? job->ctx->out_ci[c].maxcode : 0;
-      launch<PostBody>(pp, rows * W, stream);
+      { prof_scope ps(job, 4, stream); launch<PostBody>(pp, rows * W, stream); }
     }
   }
 #if !defined(IWB_EMU)
   if (cudaGetLastError() != cudaSuccess) return fail(job, "kernel launch failed");
 #endif
   return 1;
+}
+
+void iwb200_job_set_profiling(iwb200_job *job, int on) { if (job) job->profiling = on; }
+void iwb200_job_reset_stats(iwb200_job *job) {
+  if (!job) return;
+  int n; double ms;
+  iwb200_job_kernel_stats(job, 0, &n, &ms);  // drains pending events
+  for (int k = 0; k < 6; k++) { job->stat_n[k] = 0; job->stat_ms[k] = 0; }
+}
+int iwb200_job_kernel_stats(iwb200_job *job, int which, int *launches, double *total_ms) {
+  if (!job || which < 0 || which >= 6) return 0;
+#if !defined(IWB_EMU)
+  for (auto &t : job->pending) {
+    cudaEvent_t a = (cudaEvent_t)t.a, b = (cudaEvent_t)t.b;
+    cudaEventSynchronize(b);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) { job->stat_n[t.which]++; job->stat_ms[t.which] += ms; }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+  }
+#endif
+  job->pending.clear();
+  if (launches) *launches = job->stat_n[which];
+  if (total_ms) *total_ms = job->stat_ms[which];
+  return 1;
+}
+
+void iwb200_synth_xorshift(uint8_t *buf, size_t n, uint64_t seed) {
+  uint64_t s = seed;
+  for (size_t i = 0; i < n; i++) {
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    buf[i] = (uint8_t)(s >> 24);
+  }
+}
+uint64_t iwb200_fnv1a64(const uint8_t *buf, size_t n) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (size_t i = 0; i < n; i++) { h ^= buf[i]; h *= 0x100000001b3ull; }
+  return h;
 }
 
 int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *h_out, size_t out_bpr, int r0,

@@ -320,6 +320,19 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
 
 const char *iwb200_job_last_error(const iwb200_job *job);
 
+/* Per-kernel device timing.  When enabled, every launch of this job is bracketed by CUDA events on the launching
+ * stream; iwb200_job_kernel_stats() synchronises and returns, for kernel class `which` (0 vertical pass,
+ * 1 horizontal pass + epilogue, 2 PRNG fill, 3 error diffusion, 4 post, 5 fused tile kernel), the number of
+ * launches and their summed duration in ms since the last reset. */
+void iwb200_job_set_profiling(iwb200_job *job, int on);
+int iwb200_job_kernel_stats(iwb200_job *job, int which, int *launches, double *total_ms);
+void iwb200_job_reset_stats(iwb200_job *job);
+
+/* Deterministic synthetic input and output fingerprint used by the benchmarks and the full-size parity tests
+ * (SURVEY.md section 8c): xorshift64 noise (s^=s<<13; s^=s>>7; s^=s<<17; byte = s>>24), FNV-1a 64-bit. */
+void iwb200_synth_xorshift(uint8_t *buf, size_t n, uint64_t seed);
+uint64_t iwb200_fnv1a64(const uint8_t *buf, size_t n);
+
 /* After iw_process_image() with option "cuda:band" set: which output rows the output image holds. */
 int iwb200_get_band(struct iw_context *ctx, int *out_row0, int *out_row1);
 
