@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="context option name=value (tuning)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -235,7 +236,8 @@ def main():
     rows = configs.synth_rows(lib, cfg, seed=configs.XORSHIFT_SEED + rank)
 
     # ---------------- device-resident throughput -------------------------------------------------------
-    ctx = make_ctx(lib, cfg, rows=None, options={"cuda:device": local_rank})
+    extra = dict(o.split("=", 1) for o in args.opt)
+    ctx = make_ctx(lib, cfg, rows=None, options={"cuda:device": local_rank, **extra})
     job = dll.iwb200_job_create(ctx, local_rank)
     if not job:
         raise SystemExit("job creation failed: " + lib.errmsg(ctx))
@@ -323,7 +325,7 @@ def main():
 
     # ---------------- end to end through iw_process_image on host buffers ------------------------------
     def e2e_once():
-        c = make_ctx(lib, cfg, rows=rows, options={"cuda:device": local_rank})
+        c = make_ctx(lib, cfg, rows=rows, options={"cuda:device": local_rank, **extra})
         t0 = time.perf_counter()
         ok = lib.iw_process_image(c)
         dt = time.perf_counter() - t0

@@ -40,6 +40,9 @@ void *iw_malloc_large(struct iw_context *ctx, size_t n1, size_t n2) {
     iw_set_error(ctx, "Image too large to process");
     return nullptr;
   }
+  // image-sized blocks come from the page-locked pool (pipeline.cu) when the default allocator is in use
+  if (ctx->mallocfn == default_malloc && n1 * n2 >= ((size_t)1 << 20) && n1 * n2 <= ctx->max_malloc)
+    if (void *p = iwb_pinned_alloc(n1 * n2)) return p;
   return iw_malloc_ex(ctx, 0, n1 * n2);
 }
 void *iw_realloc_ex(struct iw_context *ctx, unsigned int flags, void *m, size_t oldn, size_t n) {
@@ -58,7 +61,9 @@ void *iw_realloc(struct iw_context *ctx, void *m, size_t oldn, size_t n) {
   return iw_realloc_ex(ctx, 0, m, oldn, n);
 }
 void iw_free(struct iw_context *ctx, void *mem) {
-  if (mem) ctx->freefn(ctx->userdata, mem);
+  if (!mem) return;
+  if (ctx->mallocfn == default_malloc && iwb_pinned_free(mem)) return;
+  ctx->freefn(ctx->userdata, mem);
 }
 char *iw_strdup(struct iw_context *ctx, const char *s) {
   if (!s) return nullptr;

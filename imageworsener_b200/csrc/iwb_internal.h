@@ -141,6 +141,10 @@ struct iw_context {
   iwb_timings timings;
 };
 
+// ---- page-locked host pool (pipeline.cu) ----
+void *iwb_pinned_alloc(size_t n);   // nullptr when unavailable
+bool iwb_pinned_free(void *p);      // true if p belonged to the pool
+
 // ---- api.cpp ----
 int iwb_imgtype_alpha_index(int t);
 const char *iwb_option(const iw_context *ctx, const char *name);

@@ -29,12 +29,25 @@ static unsigned long long g_launches = 0;
 #include <cuda_runtime.h>
 typedef cudaStream_t iwb_stream;
 static const char *dev_check(cudaError_t e) { return e == cudaSuccess ? nullptr : cudaGetErrorString(e); }
+// Device memory comes from CUDA's stream-ordered pool (cudaMallocAsync on the default stream) with the release
+// threshold raised, so that consecutive iw_process_image() calls reuse the same HBM blocks instead of paying
+// cudaMalloc/cudaFree (milliseconds, and an implicit device sync) every time.
+static void dev_pool_init(int device) {
+  static bool done[64] = {false};
+  if (device < 0 || device >= 64 || done[device]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[device] = true;
+}
 static void *dev_alloc(size_t n, std::string &err) {
   void *p = nullptr;
-  if (const char *m = dev_check(cudaMalloc(&p, n ? n : 1))) { err = std::string("cudaMalloc: ") + m; return nullptr; }
+  if (const char *m = dev_check(cudaMallocAsync(&p, n ? n : 1, 0))) { err = std::string("cudaMallocAsync: ") + m; return nullptr; }
   return p;
 }
-static void dev_free(void *p) { if (p) cudaFree(p); }
+static void dev_free(void *p) { if (p) cudaFreeAsync(p, 0); }
 static bool dev_h2d(void *d, const void *h, size_t n, iwb_stream s, std::string &err) {
   if (const char *m = dev_check(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s))) { err = std::string("H2D copy: ") + m; return false; }
   return true;
@@ -78,6 +91,7 @@ static bool dev_select(int device, std::string &err) {
   }
   if (device < 0 || device >= count) { err = "invalid CUDA device ordinal"; return false; }
   if (const char *m = dev_check(cudaSetDevice(device))) { err = std::string("cudaSetDevice: ") + m; return false; }
+  dev_pool_init(device);
   return true;
 }
 #else
@@ -96,6 +110,68 @@ static bool dev_select(int, std::string &) { return true; }
 #endif
 
 bool iwb_bkgd_is_translucent(const iw_context *ctx);  // plan.cpp
+
+// ------------------------------------------------------------------------------------------------------
+// Pinned host pool behind iw_malloc_large()/iw_free() (api.cpp).  Image buffers handed to and returned by the
+// library are page-locked and recycled across contexts, so H2D/D2H run as DMA at PCIe speed and no
+// cudaHostAlloc is paid per image.  Only used with the default allocator; disable with IWB200_PINNED=0.
+// ------------------------------------------------------------------------------------------------------
+#include <map>
+#include <mutex>
+static std::mutex g_pin_mu;
+static std::multimap<size_t, void *> g_pin_free;   // size -> block
+static std::map<void *, size_t> g_pin_all;         // every live pinned block -> size
+static size_t g_pin_cached = 0;
+
+void *iwb_pinned_alloc(size_t n) {
+#if defined(IWB_EMU)
+  (void)n;
+  return nullptr;
+#else
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char *e = getenv("IWB200_PINNED");
+    int count = 0;
+    enabled = !(e && e[0] == '0') && cudaGetDeviceCount(&count) == cudaSuccess && count > 0;
+  }
+  if (!enabled) return nullptr;
+  size_t want = (n + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    auto it = g_pin_free.lower_bound(want);
+    if (it != g_pin_free.end() && it->first <= want + want / 4) {
+      void *p = it->second;
+      g_pin_cached -= it->first;
+      g_pin_free.erase(it);
+      return p;
+    }
+  }
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  g_pin_all[p] = want;
+  return p;
+#endif
+}
+
+bool iwb_pinned_free(void *p) {
+#if defined(IWB_EMU)
+  (void)p;
+  return false;
+#else
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  auto it = g_pin_all.find(p);
+  if (it == g_pin_all.end()) return false;
+  if (g_pin_cached + it->second > ((size_t)16 << 30)) {  // keep at most 16 GiB page-locked and idle
+    cudaFreeHost(p);
+    g_pin_all.erase(it);
+    return true;
+  }
+  g_pin_free.emplace(it->second, p);
+  g_pin_cached += it->second;
+  return true;
+#endif
+}
 
 // ------------------------------------------------------------------------------------------------------
 struct iwb200_job {
@@ -121,6 +197,9 @@ struct iwb200_job {
   iwb_affine_t *d_jump = nullptr;
   double errdiff_m[4][12];
   iwb200_job_info info{};
+  int building_channel = 0;
+  std::vector<double> thr_host[4];
+  std::vector<double> nc_host;              // nearest-colour midpoints (when that table exists)          // per processed channel: level thresholds (table-mode channels)
 
   // scratch, sized for `chunk_rows` output rows
   int chunk_rows = 0;
@@ -140,16 +219,41 @@ struct iwb200_job {
   void *d_in = nullptr; size_t d_in_bytes = 0;
   void *d_out = nullptr; size_t d_out_bytes = 0;
 #if !defined(IWB_EMU)
-  FusedPlan fused;
+  FastPlan fused;
 #endif
 
+  // All plan tables (weight lists, colour tables, schedules) are packed into a few arena chunks and copied
+  // to the device with one H2D per chunk (flush_tables) instead of one allocation + copy per table.
+  struct chunk { std::vector<uint8_t> host; uint8_t *dev; size_t used, cap; };
+  std::vector<chunk> chunks;
   template <class T>
   T *upload(const T *h, size_t count) {
-    void *d = dev_alloc(count * sizeof(T), err);
-    if (!d) return nullptr;
-    allocs.push_back(d);
-    if (count && !dev_h2d(d, h, count * sizeof(T), 0, err)) return nullptr;
-    return (T *)d;
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    if (chunks.empty() || chunks.back().used + bytes > chunks.back().cap) {
+      chunk c;
+      c.cap = bytes > ((size_t)4 << 20) ? bytes : ((size_t)4 << 20);
+      c.dev = (uint8_t *)dev_alloc(c.cap, err);
+      if (!c.dev) return nullptr;
+      allocs.push_back(c.dev);
+      c.host.resize(c.cap);
+      c.used = 0;
+      chunks.push_back(std::move(c));
+    }
+    chunk &c = chunks.back();
+    if (count) memcpy(c.host.data() + c.used, h, count * sizeof(T));
+    T *d = (T *)(c.dev + c.used);
+    c.used += bytes;
+    return d;
+  }
+  bool flush_tables() {
+    for (chunk &c : chunks) {
+      if (c.used && !dev_h2d(c.dev, c.host.data(), c.used, 0, err)) return false;
+      // pageable source: the copy is staged before cudaMemcpyAsync returns, so the host copy can go
+      std::vector<uint8_t>().swap(c.host);
+      c.cap = c.used;  // closed
+    }
+    return true;
   }
   void *scratch(size_t bytes) {
     void *d = dev_alloc(bytes, err);
@@ -248,6 +352,7 @@ bool build_output_tables(iwb200_job *job, const iw_context *ctx, const iwb_out_c
     }
   }
   o->ntab = (int)thr.size();
+  job->thr_host[job->building_channel] = thr;
   o->thr = job->upload(thr.data(), thr.size());
   o->codeval = job->upload(code.data(), code.size());
   o->linval = job->upload(lin.data(), lin.size());
@@ -256,6 +361,322 @@ bool build_output_tables(iwb200_job *job, const iw_context *ctx, const iwb_out_c
 }
 
 }  // namespace
+
+
+// ------------------------------------------------------------------------------------------------------
+// Fast path, host side: streaming schedules, eligibility, launches (kernels in fused.cuh)
+// ------------------------------------------------------------------------------------------------------
+#if !defined(IWB_EMU)
+namespace {
+
+struct HostSched {
+  int S = 0, max_emit = 0;
+  std::vector<double> w;
+  std::vector<int> emit_lo, emit_n, first, last;
+};
+
+// Turn a tap list into the per-input streaming schedule.  Only lists whose windows are contiguous runs of real
+// source samples, non-empty and monotone qualify (the STANDARD edge policy away from degenerate cases);
+// anything else stays on the generic kernels.
+bool build_sched(const iwb_axis_table &t, int max_slots, HostSched *hs) {
+  if (t.mode != 0 || t.n_out < 1) return false;
+  const int n_in = t.n_in, n_out = t.n_out;
+  hs->first.resize(n_out);
+  hs->last.resize(n_out);
+  for (int o = 0; o < n_out; o++) {
+    const int a = t.first[o], b = t.first[o + 1];
+    if (b <= a) return false;
+    if (t.src[a] < 0) return false;
+    for (int k = a + 1; k < b; k++)
+      if (t.src[k] != t.src[k - 1] + 1) return false;
+    hs->first[o] = t.src[a];
+    hs->last[o] = t.src[b - 1];
+    if (hs->last[o] >= n_in) return false;
+    if (o && (hs->first[o] < hs->first[o - 1] || hs->last[o] < hs->last[o - 1])) return false;
+  }
+  // most windows open at once
+  int S = 1;
+  for (int o = 0, lo = 0; o < n_out; o++) {
+    while (hs->last[lo] < hs->first[o]) lo++;
+    S = std::max(S, o - lo + 1);
+  }
+  if (S > max_slots) return false;
+  static const int sizes[] = {2, 3, 4, 5, 6, 8, 12, 16};
+  int SS = 0;
+  for (int v : sizes)
+    if (v >= S) { SS = v; break; }
+  if (!SS) return false;
+  hs->S = SS;
+  hs->w.assign((size_t)n_in * SS, 0.0);
+  hs->emit_lo.assign(n_in, 0);
+  hs->emit_n.assign(n_in, 0);
+  for (int o = 0; o < n_out; o++) {
+    const int a = t.first[o], b = t.first[o + 1];
+    for (int k = a; k < b; k++) hs->w[(size_t)t.src[k] * SS + (o % SS)] = t.w[k];
+    const int r = hs->last[o];
+    if (hs->emit_n[r] == 0) hs->emit_lo[r] = o;
+    hs->emit_n[r]++;
+    hs->max_emit = std::max(hs->max_emit, hs->emit_n[r]);
+  }
+  return true;
+}
+
+bool upload_sched(iwb200_job *job, const HostSched &hs, int n_in, int n_out, AxisSched *d) {
+  d->S = hs.S; d->n_in = n_in; d->n_out = n_out;
+  d->w = job->upload(hs.w.data(), hs.w.size());
+  d->emit_lo = job->upload(hs.emit_lo.data(), hs.emit_lo.size());
+  d->emit_n = job->upload(hs.emit_n.data(), hs.emit_n.size());
+  d->first = job->upload(hs.first.data(), hs.first.size());
+  d->last = job->upload(hs.last.data(), hs.last.size());
+  return d->w && d->emit_lo && d->emit_n && d->first && d->last;
+}
+
+template <int S, int NC>
+void launch_v(const VStreamParams &p, dim3 grid, size_t smem, iwb_stream st) {
+  // the cp.async ring moves 4 bytes per thread and row: needs NC == 4 and 4-byte aligned rows
+  const bool ring = NC == 4 && (p.bpr % 4 == 0) && (((uintptr_t)p.src + p.x0_bytes) % 4 == 0) && (p.ncols % 4 == 0);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(iwb_vstream<S, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(iwb_vstream<S, NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  if (ring) iwb_vstream<S, NC, true><<<grid, IWB_V_THREADS, smem, st>>>(p);
+  else iwb_vstream<S, NC, false><<<grid, IWB_V_THREADS, smem, st>>>(p);
+}
+template <int S, int NCH>
+void launch_h(const HStreamParams &p, dim3 grid, size_t smem, iwb_stream st) {
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(iwb_hstream<S, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  iwb_hstream<S, NCH><<<grid, 32 * IWB_H_WARPS, smem, st>>>(p);
+}
+
+template <int NC>
+bool dispatch_v_nc(int S, const VStreamParams &p, dim3 g, size_t sm, iwb_stream st) {
+  switch (S) {
+    case 2: launch_v<2, NC>(p, g, sm, st); return true;
+    case 3: launch_v<3, NC>(p, g, sm, st); return true;
+    case 4: launch_v<4, NC>(p, g, sm, st); return true;
+    case 5: launch_v<5, NC>(p, g, sm, st); return true;
+    case 6: launch_v<6, NC>(p, g, sm, st); return true;
+    case 8: launch_v<8, NC>(p, g, sm, st); return true;
+  }
+  return false;
+}
+bool dispatch_v(int S, int NC, const VStreamParams &p, dim3 g, size_t sm, iwb_stream st) {
+  if (NC == 4) return dispatch_v_nc<4>(S, p, g, sm, st);
+  if (NC == 2) {
+    if (S == 12) { launch_v<12, 2>(p, g, sm, st); return true; }
+    if (S == 16) { launch_v<16, 2>(p, g, sm, st); return true; }
+  }
+  return false;
+}
+template <int NCH>
+bool dispatch_h_nch(int S, const HStreamParams &p, dim3 g, size_t sm, iwb_stream st) {
+  switch (S) {
+    case 2: launch_h<2, NCH>(p, g, sm, st); return true;
+    case 3: launch_h<3, NCH>(p, g, sm, st); return true;
+    case 4: launch_h<4, NCH>(p, g, sm, st); return true;
+    case 5: launch_h<5, NCH>(p, g, sm, st); return true;
+    case 6: launch_h<6, NCH>(p, g, sm, st); return true;
+    case 8: launch_h<8, NCH>(p, g, sm, st); return true;
+    case 12: launch_h<12, NCH>(p, g, sm, st); return true;
+    case 16: launch_h<16, NCH>(p, g, sm, st); return true;
+  }
+  return false;
+}
+bool dispatch_h(int S, int NCH, const HStreamParams &p, dim3 g, size_t sm, iwb_stream st) {
+  if (NCH == 1) return dispatch_h_nch<1>(S, p, g, sm, st);
+  if (NCH == 3) return dispatch_h_nch<3>(S, p, g, sm, st);
+  return false;
+}
+
+// nr/nb: input samples of the longest strip/segment; nout: outputs tracked (strip/segment + still-open predecessors)
+size_t v_smem_bytes(int nr, int S, int nout, int nc) {
+  return (size_t)256 * 16 * 8 + (size_t)nr * S * 8 + (size_t)((nout + 3) & ~3) * 4 + (size_t)IWB_RING_D * IWB_V_THREADS * 4 +
+         (size_t)8 * nc * IWB_V_THREADS * 4 + 16;
+}
+size_t h_smem_bytes(int nb, int S, int nch, int nout) {
+  size_t b = (size_t)nb * S * 8;
+  b += (size_t)IWB_H_WARPS * S * nch * 32 * 8;      // parked samples
+  b += (size_t)nch * 256 * 8;                       // float2 level bounds
+  b += 128 * 4;                                     // ordered-dither thresholds
+  b += (size_t)IWB_RING_D * nch * IWB_H_THREADS * 4;
+  b += (size_t)nout * 4;
+  b += (size_t)(nch * 1026 + ((nch * 1026) & 1)) * 2;
+  b += (size_t)IWB_H_WARPS * 32 * IWB_OSTAGE_PITCH;
+  return b + 16;
+}
+
+}  // namespace
+
+// Decide whether this job can use the streaming kernels and, if so, build and upload their schedules.
+static void fused_plan_build(iwb200_job *job, FastPlan *f) {
+  iw_context *ctx = job->ctx;
+  f->enabled = 0;
+  const int nch = ctx->in_nch_phys;
+  if (ctx->img1.sampletype != IW_SAMPLETYPE_UINT || ctx->img1.bit_depth != 8) return;
+  if ((ctx->img1.orient_transform & 7) != 0) return;
+  if (nch != 1 && nch != 3) return;
+  if (ctx->in_type_logical != ctx->img1.imgtype) return;
+  if (job->nproc != nch || ctx->out_nch != nch || job->has_alpha) return;
+  if (ctx->img2.sampletype != IW_SAMPLETYPE_UINT || ctx->img2.bit_depth != 8) return;
+  if (job->any_errdiff) return;
+  if (ctx->axis[0].per_channel_tables || ctx->axis[1].per_channel_tables) return;
+  for (int p = 0; p < nch; p++) {
+    const iwb_mid_channel &mc = ctx->mid_ci[job->mid_index[p]];
+    if (job->mid_index[p] != p || mc.in_channel != p || mc.out_channel != p || mc.to_gray || mc.premultiplied) return;
+    if (job->cin[p].early_bkgd || job->cin[p].lut[0] != job->cin[0].lut[0] || !job->cin[p].lut[0]) return;
+  }
+  HostSched hv, hh;
+  if (!build_sched(job->vtab[0], 16, &hv)) return;
+  if (!build_sched(job->htab[0], 16, &hh)) return;
+  if (hh.S * nch > 48) return;
+  f->NC = hv.S <= 8 ? 4 : 2;
+  f->nch = nch;
+  f->SV = hv.S;
+  f->SH = hh.S;
+  const int ncols = job->in_w * nch;
+  // chunk of output rows per kernel pair (bounds the intermediate; it is written and re-read through L2)
+  size_t chunk_mb = 512;
+  if (const char *o = iwb_option(ctx, "cuda:chunk_mb")) chunk_mb = (size_t)std::max(1, atoi(o));
+  size_t rows = (chunk_mb << 20) / ((size_t)ncols * 4);
+  rows = std::max<size_t>(rows, 128);
+  rows = (rows / 128) * 128;
+  rows = std::min<size_t>(rows, (size_t)((job->out.height + 127) / 128) * 128);
+  f->chunk_rows = (int)rows;
+  f->pitch_j = rows;
+  if (const char *o = iwb_option(ctx, "cuda:strip")) f->strip = std::max(8, atoi(o) & ~7);
+  if (const char *o = iwb_option(ctx, "cuda:seg")) f->seg = std::max(4, atoi(o) & ~3);
+  // shared-memory needs: longest input range of any strip / segment
+  auto longest = [](const std::vector<int> &first, const std::vector<int> &last, int step) {
+    int m = 0, n = (int)first.size();
+    for (int o0 = 0; o0 < n; o0 += step) {
+      int o1 = std::min(n, o0 + step);
+      m = std::max(m, last[o1 - 1] - first[o0] + 1);
+    }
+    return m;
+  };
+  // strips restart at every chunk boundary, so bound by any window of `strip` consecutive outputs
+  auto longest_any = [](const std::vector<int> &first, const std::vector<int> &last, int step) {
+    int m = 0, n = (int)first.size();
+    for (int o0 = 0; o0 < n; o0++) {
+      int o1 = std::min(n, o0 + step);
+      m = std::max(m, last[o1 - 1] - first[o0] + 1);
+    }
+    return m;
+  };
+  (void)longest;
+  while (true) {
+    f->v_nr_max = longest_any(hv.first, hv.last, f->strip);
+    f->v_smem = v_smem_bytes(f->v_nr_max, f->SV, f->strip + f->SV, f->NC);
+    if (f->v_smem <= 96 * 1024 || f->strip <= 4) break;
+    f->strip /= 2;
+  }
+  while (true) {
+    f->h_nb_max = longest_any(hh.first, hh.last, f->seg);
+    f->h_smem = h_smem_bytes(f->h_nb_max, f->SH, nch, f->seg + f->SH);
+    if (f->h_smem <= 160 * 1024 || f->seg <= 8) break;
+    f->seg = (f->seg / 2) & ~3;
+  }
+  if (f->v_smem > 200 * 1024 || f->h_smem > 200 * 1024) return;
+  if (!upload_sched(job, hv, job->in_h, job->out.height, &f->sv)) return;
+  if (!upload_sched(job, hh, job->in_w, job->out.width, &f->sh)) return;
+  f->lut = job->cin[0].lut[0];
+  for (int p = 0; p < nch; p++) {
+    const DevChanOut &o = job->cout[p];
+    FastQuant &q = f->fq[p];
+    q = FastQuant();
+    // level bounds [lo, hi) in linear space: thresholds (dithered / nearest-by-distance) or colour midpoints
+    std::vector<double> lo, hi;
+    if (o.use_nc) {
+      q.mode = 2;
+      lo.resize(256); hi.resize(256);
+      for (int c = 0; c < 256; c++) { lo[c] = c ? job->nc_host[c - 1] : 0.0; hi[c] = c < 255 ? job->nc_host[c] : 2.0; }
+    } else if (o.qmode == 1 && o.color_count == 0 && o.ntab <= 256 && (o.dfamily == 0 || o.dfamily == 1 || o.dfamily == 3)) {
+      q.mode = 1;
+      const std::vector<double> &thr = job->thr_host[p];
+      lo.assign(thr.begin(), thr.end());
+      hi.resize(thr.size());
+      for (size_t k = 0; k < thr.size(); k++) hi[k] = k + 1 < thr.size() ? thr[k + 1] : 2.0;
+    } else {
+      continue;   // linear-space arithmetic, posterisation: exact generic quantiser
+    }
+    const int n = (int)lo.size();
+    q.top = n - 1;
+    std::vector<float2> pairs(n);
+    double worst = 1.0;
+    for (int k = 0; k < n; k++) {
+      pairs[k] = make_float2((float)lo[k], (float)hi[k]);
+      if (k < n - 1 && hi[k] > lo[k]) worst = std::max(worst, hi[k] / (hi[k] - lo[k]));
+    }
+    // FP32 rounding of s, lo, hi (2^-24 each) and of the quotient, amplified by hi/(hi-lo); x8 safety
+    q.margin = q.mode == 1 ? (float)(2e-6 + 8.0 * 2.4e-7 * worst) : (float)(8.0 * 1.2e-7);
+    if (q.mode == 1 && q.margin > 0.004f) { q = FastQuant(); continue; }
+    const int nh = 1024;
+    std::vector<uint16_t> hint(nh + 2);
+    int lev = 0;
+    for (int i = 0; i <= nh; i++) {
+      const double sv = (double)i / (double)nh;
+      while (lev + 1 < n && lo[lev + 1] <= sv) lev++;
+      // the float search only walks upward, so start one level low when the float bound rounds above i/nh
+      int start = lev;
+      while (start > 0 && (double)pairs[start].x > sv) start--;
+      hint[i] = (uint16_t)start;
+    }
+    hint[nh + 1] = hint[nh];
+    q.nhint = nh;
+    q.pairs = job->upload(pairs.data(), pairs.size());
+    q.hint = job->upload(hint.data(), hint.size());
+    if (!q.pairs || !q.hint) return;
+  }
+  f->vfirst = hv.first;
+  f->vlast = hv.last;
+  f->enabled = 1;
+}
+
+static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const DevOutput &out, int r0, int r1,
+                      iwb_stream stream) {
+  if (!f->interT) {
+    f->interT = (float *)job->scratch((size_t)job->in_w * f->nch * f->pitch_j * sizeof(float));
+    if (!f->interT) return false;
+  }
+  const int nch = f->nch;
+  for (int c0 = r0; c0 < r1; c0 += f->chunk_rows) {
+    const int c1 = std::min(r1, c0 + f->chunk_rows);
+    VStreamParams vp;
+    vp.src = in.pix; vp.bpr = in.bpr; vp.row_origin = in.row_origin; vp.y0 = in.y0;
+    vp.x0_bytes = (size_t)in.x0 * nch; vp.ncols = job->in_w * nch; vp.lut = f->lut; vp.sc = f->sv;
+    vp.interT = f->interT; vp.pitch_j = f->pitch_j; vp.row_lo = c0; vp.row_hi = c1; vp.strip = f->strip;
+    vp.intclamp = job->cm.intclamp;
+    dim3 gv((unsigned)((vp.ncols + IWB_V_THREADS * f->NC - 1) / (IWB_V_THREADS * f->NC)), (unsigned)((c1 - c0 + f->strip - 1) / f->strip));
+    {
+      prof_scope ps(job, 5, stream);
+      if (!dispatch_v(f->SV, f->NC, vp, gv, f->v_smem, stream)) return fail(job, "fast path: no vertical kernel variant");
+      g_launches++;
+    }
+    HStreamParams hp;
+    hp.interT = f->interT; hp.pitch_j = f->pitch_j; hp.row_lo = c0; hp.row_hi = c1; hp.sc = f->sh; hp.seg = f->seg;
+    hp.out = out; hp.intclamp = job->cm.intclamp; hp.out_w = out.width; hp.jump = job->d_jump;
+    for (int p = 0; p < 4; p++) { hp.ch[p] = job->cout[p < nch ? p : 0]; hp.fq[p] = f->fq[p < nch ? p : 0]; }
+    dim3 gh((unsigned)((out.width + f->seg - 1) / f->seg), (unsigned)((c1 - c0 + 32 * IWB_H_WARPS - 1) / (32 * IWB_H_WARPS)));
+    {
+      prof_scope ps(job, 1, stream);
+      if (!dispatch_h(f->SH, nch, hp, gh, f->h_smem, stream)) return fail(job, "fast path: no horizontal kernel variant");
+      g_launches++;
+    }
+    if (job->negate) {
+      PostParams pp;
+      pp.out = out; pp.row0 = c0; pp.row1 = c1; pp.negate = 1; pp.alpha_ch = -1; pp.clear_transparent = 0;
+      for (int c = 0; c < 4; c++) pp.maxcode[c] = c < job->ctx->out_nch ? job->ctx->out_ci[c].maxcode : 0;
+      prof_scope ps(job, 4, stream);
+      launch<PostBody>(pp, (size_t)(c1 - c0) * out.width, stream);
+    }
+  }
+  if (cudaGetLastError() != cudaSuccess) return fail(job, "fast path: kernel launch failed");
+  return true;
+}
+#endif  // !IWB_EMU
 
 extern "C" {
 
@@ -347,6 +768,7 @@ static iwb200_job *job_build(iw_context *ctx, int device) {
     }
     nc_dev = job->upload(t.data(), t.size());
     if (!nc_dev) return job;
+    job->nc_host = t;
   }
 
   std::vector<lut_key> luts;
@@ -405,6 +827,7 @@ static iwb200_job *job_build(iw_context *ctx, int device) {
     // ---- output side
     DevChanOut &o = job->cout[p];
     memset(&o, 0, sizeof o);
+    job->building_channel = p;
     o.out_ch = mc.out_channel;
     o.is_alpha = is_alpha;
     o.premult = mc.premultiplied;
@@ -471,6 +894,7 @@ static iwb200_job *job_build(iw_context *ctx, int device) {
   if (!(nofuse && !strcmp(nofuse, "0"))) fused_plan_build(job, &job->fused);
   info.uses_fused_kernel = job->fused.enabled;
 #endif
+  job->flush_tables();
   return job;
 }
 
