@@ -67,6 +67,7 @@ struct HStreamParams {
   int seg;                    // outputs per CTA segment
   DevOutput out;
   DevChanOut ch[4];           // exact epilogue description (generic structure)
+  const DevChanOut *ch_g;     // the same four structs in global memory (addressable by the out-of-line exact path)
   FastQuant fq[4];
   int intclamp;
   int out_w;
@@ -84,6 +85,8 @@ struct FastPlan {
   float *interT = nullptr;
   size_t pitch_j = 0;
   int strip = 32, seg = 64;
+  int epi = 0;
+  const DevChanOut *ch_g = nullptr;
   int chunk_rows = 0;
   size_t v_smem = 0, h_smem = 0;
   int v_nr_max = 0, h_nb_max = 0;
@@ -109,10 +112,37 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // accumulator shuffling.  Input bytes arrive through a per-thread cp.async ring RING_D rows deep.
 // ---------------------------------------------------------------------------------------------------------
 #define IWB_V_THREADS 128
+#ifndef IWB_RING_D
 #define IWB_RING_D 8
+#endif
+#ifndef IWB_V_TB
+#define IWB_V_TB 8                // finished rows buffered per thread before a transposed store (8 = one 32-byte sector)
+#endif
+#ifndef IWB_V_PIPE
+#define IWB_V_PIPE 0
+#endif
+#ifndef IWB_H_PIPE
+#define IWB_H_PIPE 0
+#endif
+#ifndef IWB_LUT_REP
+#define IWB_LUT_REP 16           // shared-memory copies of the colour table: one per lane of a half-warp (conflict free)
+#endif
+#ifndef IWB_V_MINBLOCKS
+#define IWB_V_MINBLOCKS 4
+#endif
 
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src));
+}
+
+// NC byte columns per thread (8 when rows are 8-byte aligned: the per-row overhead -- weights, ring, loop -- is
+// then amortised over 8*S accumulator updates).  RING: input through the cp.async ring (needs NC in {4,8} and
+// aligned rows); otherwise plain loads.  TB: finished rows buffered per thread before a transposed store.
 template <int S, int NC, bool RING>
-__global__ void __launch_bounds__(IWB_V_THREADS) iwb_vstream(const VStreamParams p) {
+__global__ void __launch_bounds__(IWB_V_THREADS, (NC >= 8 ? 3 : IWB_V_MINBLOCKS)) iwb_vstream(const VStreamParams p) {
+  constexpr int NW = NC >= 4 ? NC / 4 : 1;                // 32-bit ring words per thread and row
+  constexpr int TB = IWB_V_TB;                            // rows per transposed store group
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int o0 = p.row_lo + blockIdx.y * p.strip;
   const int o1 = min(o0 + p.strip, p.row_hi);
@@ -121,12 +151,12 @@ __global__ void __launch_bounds__(IWB_V_THREADS) iwb_vstream(const VStreamParams
   int ob = o0;                                            // first output still open at r0
   while (ob > 0 && p.sc.last[ob - 1] >= r0) ob--;
   const int nout = o1 - ob;
-  double *lut_s = (double *)smem_raw;                     // [256][16]
-  double *w_s = lut_s + 256 * 16;                         // [nr][S]
+  double *lut_s = (double *)smem_raw;                     // [256][IWB_LUT_REP]
+  double *w_s = lut_s + 256 * IWB_LUT_REP;                // [nr][S]
   int *last_s = (int *)(w_s + (size_t)nr * S);            // [nout] last input row of each output, relative to r0
-  unsigned *ring = (unsigned *)(last_s + ((nout + 3) & ~3));   // [RING_D][threads]
-  float *tbuf = (float *)(ring + IWB_RING_D * IWB_V_THREADS);  // [8][NC][threads] finished rows awaiting a sector
-  for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) lut_s[i] = p.lut[i >> 4];
+  unsigned *ring = (unsigned *)(last_s + ((nout + 3) & ~3));          // [RING_D][threads][NW]
+  float *tbuf = (float *)(ring + IWB_RING_D * IWB_V_THREADS * NW);    // [TB][NC][threads]
+  for (int i = threadIdx.x; i < 256 * IWB_LUT_REP; i += blockDim.x) lut_s[i] = p.lut[i / IWB_LUT_REP];
   for (int i = threadIdx.x; i < nr * S; i += blockDim.x) w_s[i] = p.sc.w[(size_t)r0 * S + i];
   for (int i = threadIdx.x; i < nout; i += blockDim.x) last_s[i] = p.sc.last[ob + i] - r0;
   __syncthreads();
@@ -134,9 +164,10 @@ __global__ void __launch_bounds__(IWB_V_THREADS) iwb_vstream(const VStreamParams
   const int col0 = (blockIdx.x * blockDim.x + threadIdx.x) * NC;
   if (col0 >= p.ncols) return;
   const bool full = col0 + NC <= p.ncols;
-  const int rep = threadIdx.x & 15;
+  const double *lut_t = lut_s + (threadIdx.x % IWB_LUT_REP);   // this lane's bank pair
   const uint8_t *colp = p.src + (size_t)(p.y0 + r0 - p.row_origin) * p.bpr + p.x0_bytes + col0;
-  unsigned *myring = ring + threadIdx.x;
+  unsigned *myring = ring + threadIdx.x * NW;
+  constexpr int RSTRIDE = IWB_V_THREADS * NW;             // words between ring slots
 
   double acc[S][NC];
 #pragma unroll
@@ -144,40 +175,66 @@ __global__ void __launch_bounds__(IWB_V_THREADS) iwb_vstream(const VStreamParams
 #pragma unroll
     for (int c = 0; c < NC; c++) acc[s][c] = 0.0;
 
+  const uint8_t *gnext = colp;                            // next row to request
+  int requested = 0;
+  auto request = [&]() {
+    if (requested < nr) {
+      if (NW == 2) cp_async8(myring + (requested % IWB_RING_D) * RSTRIDE, gnext);
+      else cp_async4(myring + (requested % IWB_RING_D) * RSTRIDE, gnext);
+      gnext += p.bpr;
+    }
+    requested++;
+    cp_async_commit();
+  };
   if (RING) {
 #pragma unroll
-    for (int d = 0; d < IWB_RING_D - 1; d++) {
-      if (d < nr) cp_async4(myring + d * IWB_V_THREADS, colp + (size_t)d * p.bpr);
-      cp_async_commit();
-    }
+    for (int d = 0; d < IWB_RING_D - 1; d++) request();
   }
 
   int i = 0;                                              // next input row (relative to r0)
-  auto row_step = [&]() {
+  int fetched = 0;                                        // rows whose values have been looked up
+  const double *wr = w_s;
+  // look up the linear values of row `fetched` (software pipelined one row ahead of the arithmetic, so the
+  // ring read -> unpack -> table read chain never sits in front of the FP64 block that needs it)
+  auto fetch = [&](double (&v)[NC]) {
     unsigned code[NC];
     if (RING) {
-      const int ahead = i + IWB_RING_D - 1;
-      if (ahead < nr) cp_async4(myring + (ahead % IWB_RING_D) * IWB_V_THREADS, colp + (size_t)ahead * p.bpr);
-      cp_async_commit();
+      request();
       cp_async_wait<IWB_RING_D - 1>();
-      const unsigned v = myring[(i % IWB_RING_D) * IWB_V_THREADS];
+      const unsigned *slot = myring + (fetched % IWB_RING_D) * RSTRIDE;
 #pragma unroll
-      for (int c = 0; c < NC; c++) code[c] = (v >> (8 * c)) & 0xff;
+      for (int wd = 0; wd < NW; wd++) {
+        const unsigned x = slot[wd];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+          if (wd * 4 + c < NC) code[wd * 4 + c] = (x >> (8 * c)) & 0xff;
+      }
     } else {
-      const uint8_t *q = colp + (size_t)i * p.bpr;
+      const uint8_t *q = colp + (size_t)min(fetched, nr - 1) * p.bpr;
 #pragma unroll
       for (int c = 0; c < NC; c++) code[c] = (col0 + c < p.ncols) ? __ldg(q + c) : 0u;
     }
-    double v[NC];
 #pragma unroll
-    for (int c = 0; c < NC; c++) v[c] = lut_s[code[c] * 16 + rep];
-    const double *wr = w_s + (size_t)i * S;
+    for (int c = 0; c < NC; c++) v[c] = lut_t[code[c] * IWB_LUT_REP];
+    fetched++;
+  };
+  double vcur[NC];
+  if (IWB_V_PIPE) fetch(vcur);
+  auto row_step = [&]() {
+    double vnext[NC];
+    if (IWB_V_PIPE) fetch(vnext);                         // row i+1 (a harmless re-read past the last row)
+    else fetch(vcur);
 #pragma unroll
     for (int s = 0; s < S; s++) {
       const double w = wr[s];
 #pragma unroll
-      for (int c = 0; c < NC; c++) acc[s][c] = __dadd_rn(acc[s][c], __dmul_rn(v[c], w));
+      for (int c = 0; c < NC; c++) acc[s][c] = __dadd_rn(acc[s][c], __dmul_rn(vcur[c], w));
     }
+    if (IWB_V_PIPE) {
+#pragma unroll
+      for (int c = 0; c < NC; c++) vcur[c] = vnext[c];
+    }
+    wr += S;
     i++;
   };
 
@@ -190,30 +247,27 @@ __global__ void __launch_bounds__(IWB_V_THREADS) iwb_vstream(const VStreamParams
         while (i <= iend) row_step();
         if (o >= o0) {
           const int orel = o - p.row_lo;
-          float f[NC];
+          if (p.intclamp) {
 #pragma unroll
-          for (int c = 0; c < NC; c++) {
-            double a = acc[k][c];
-            if (p.intclamp) a = a < 0.0 ? 0.0 : (a > 1.0 ? 1.0 : a);
-            f[c] = (float)a;
+            for (int c = 0; c < NC; c++) acc[k][c] = acc[k][c] < 0.0 ? 0.0 : (acc[k][c] > 1.0 ? 1.0 : acc[k][c]);
           }
 #pragma unroll
-          for (int c = 0; c < NC; c++) tbuf[((orel & 7) * NC + c) * IWB_V_THREADS + threadIdx.x] = f[c];
-          if ((orel & 7) == 7 || o == o1 - 1) {            // a full 8-row group (one 32-byte sector per column)
-            const int base = orel & ~7, cnt = (orel & 7) + 1;
+          for (int c = 0; c < NC; c++) tbuf[((orel % TB) * NC + c) * IWB_V_THREADS + threadIdx.x] = (float)acc[k][c];
+          if ((orel % TB) == TB - 1 || o == o1 - 1) {      // a full group: TB consecutive rows of each column
+            const int base = orel - (orel % TB), cnt = (orel % TB) + 1;
 #pragma unroll
             for (int c = 0; c < NC; c++) {
-              if (col0 + c < p.ncols) {
+              if (full || col0 + c < p.ncols) {
                 float *dst = p.interT + (size_t)(col0 + c) * p.pitch_j + base;
-                float g[8];
+                float g[TB];
 #pragma unroll
-                for (int r = 0; r < 8; r++) g[r] = tbuf[(r * NC + c) * IWB_V_THREADS + threadIdx.x];
-                if (cnt == 8) {
-                  reinterpret_cast<float4 *>(dst)[0] = make_float4(g[0], g[1], g[2], g[3]);
-                  reinterpret_cast<float4 *>(dst)[1] = make_float4(g[4], g[5], g[6], g[7]);
+                for (int r = 0; r < TB; r++) g[r] = tbuf[(r * NC + c) * IWB_V_THREADS + threadIdx.x];
+                if (cnt == TB) {
+#pragma unroll
+                  for (int r = 0; r < TB; r += 4) *reinterpret_cast<float4 *>(dst + r) = make_float4(g[r], g[r + 1], g[r + 2], g[r + 3]);
                 } else {
 #pragma unroll
-                  for (int r = 0; r < 8; r++)
+                  for (int r = 0; r < TB; r++)
                     if (r < cnt) dst[r] = g[r];
                 }
               }
@@ -231,53 +285,78 @@ __global__ void __launch_bounds__(IWB_V_THREADS) iwb_vstream(const VStreamParams
 // ---------------------------------------------------------------------------------------------------------
 // horizontal streaming kernel + quantise/dither epilogue
 //
-// Same phase structure; lanes = 32 different rows so the schedule is warp-uniform.  Because the vertical kernel
-// stores the intermediate transposed, lane j reads interT[column][row j]: 32 lanes = one 128-byte line, fetched
-// by a per-thread cp.async ring IWB_RING_D columns deep (no staging, no barriers).  A finished sample is parked
-// in shared memory; after each cycle of S phases ONE copy of the epilogue code quantises the parked samples in
-// increasing output order (random dither consumes its draws in that order) and puts the bytes into a staging
-// tile that is flushed as coalesced row segments.
+// Same phase structure; lanes = different rows so the schedule is warp-uniform, R rows per thread (a warp covers
+// 32*R rows) so that one weight fetch and one loop iteration feed R*NCH*S accumulator updates.  Because the
+// vertical kernel stores the intermediate transposed, lane j reads interT[column][row j]: 32 lanes = one
+// 128-byte line, fetched by a per-thread cp.async ring IWB_RING_D columns deep (no staging, no barriers).
+// A finished sample is parked in shared memory; after each cycle of S phases ONE copy of the epilogue code
+// quantises the parked samples in increasing output order (random dither consumes its draws in that order) and
+// puts the bytes into a staging tile that is flushed as coalesced row segments.
 //
 // Epilogue fast path: level search and dither decision in FP32 against float copies of the
 // host tables; whenever the FP32 fraction is within `margin` of the decision threshold (a few 1e-4 of the
 // samples) the exact FP64 quantiser of kernels.cuh decides instead, so stored codes are bit-identical.
+// EPI = 1: every channel is in threshold-table mode with the same dither family; EPI = 2: every channel uses the
+// nearest-colour midpoint table; EPI = 0: anything else, decided per sample at run time.
 // ---------------------------------------------------------------------------------------------------------
-#define IWB_H_WARPS 4
+#ifndef IWB_H_WARPS
+#define IWB_H_WARPS 8
+#endif
 #define IWB_H_THREADS (32 * IWB_H_WARPS)
 #define IWB_OSTAGE_PITCH 132   // bytes per staging row (33 words: lane-private banks)
 
-__device__ __noinline__ double exact_quantise(const DevChanOut &o, double s, int x, int y, uint32_t draw) {
-  return quantise(o, s, x, y, draw);
+__device__ __noinline__ int exact_quantise(const DevChanOut *o, double s, int x, int y, uint32_t draw) {
+  return (int)(0.5 + quantise(*o, s, x, y, draw));
 }
 
-__device__ __forceinline__ int quantise8_fast(const DevChanOut &o, const FastQuant &fq, const float2 *pairs_s,
-                                              const uint16_t *hint_s, const float *ordf_s, double s, int x, int y,
+// FP32 level search: largest level whose float lower bound is <= sf, starting from the bucket hint
+__device__ __forceinline__ int level_of(const float2 *pairs_s, const uint16_t *hint_s, float sf, int top, float2 *pr) {
+  int q = hint_s[(int)(sf * 1024.0f)];
+  float2 v = pairs_s[q];
+  while (v.y <= sf && q < top) { q++; v = pairs_s[q]; }
+  *pr = v;
+  return q;
+}
+
+// EPI: 0 = per-sample run-time choice (mixed channels); 1 = threshold tables, no dither; 2 = nearest-colour
+// midpoints; 3 = threshold tables, ordered dither; 4 = threshold tables, random dither.
+template <int EPI>
+__device__ __forceinline__ int quantise8_fast(const DevChanOut &o, const DevChanOut *og, const FastQuant &fq, const float2 *pairs_s,
+                                              const uint16_t *hint_s, const float *ordrow, double s, int x, int y,
                                               uint32_t draw) {
-  if (fq.mode == 0) return (int)(0.5 + exact_quantise(o, s, x, y, draw));
-  // s <= 0 clamps to 0, which converts to exactly code 0; s above the snap point converts to exactly the top
-  // code (reference: src/imagew-main.c:684-685, :429-433, :618-621) -- both "exact", no dither decision.
-  if (!(s > 0.0)) return 0;
-  if (s > 0.999999999) return fq.top;
+  const int mode = EPI == 0 ? fq.mode : (EPI == 2 ? 2 : 1);
+  if (mode == 0) return exact_quantise(og, s, x, y, draw);
+  const int fam = EPI == 0 ? o.dfamily : (EPI == 3 ? 1 : (EPI == 4 ? 3 : 0));
   const float sf = (float)s;
-  int q = hint_s[(int)(sf * (float)fq.nhint)];
-  float2 pr = pairs_s[q];
-  while (pr.y <= sf && q < fq.top) { q++; pr = pairs_s[q]; }
-  if (fq.mode == 2) {          // nearest colour: level q holds [midpoint below, midpoint above)
-    const float d = fminf(sf - pr.x, pr.y - sf);
-    if (d > fq.margin) return q;
-    return (int)(0.5 + exact_quantise(o, s, x, y, draw));
+  // s <= 0 clamps to 0 and converts to exactly code 0; s above the snap point converts to exactly the top code
+  // (reference: src/imagew-main.c:684-685, :429-433, :618-621).  Without random dither the whole float
+  // interval that rounds to 1.0f also ends at the top code (its fraction is > 0.9999 and every threshold is
+  // <= 63.5/64), so the cheap float tests suffice; random dither keeps the exact FP64 tests.
+  if (fam == 3) {
+    if (!(s > 0.0)) return 0;
+    if (s > 0.999999999) return fq.top;
+  } else {
+    if (!(sf > 0.0f)) return 0;
+    if (sf >= 1.0f) return fq.top;
   }
-  if (q >= fq.top) return (int)(0.5 + exact_quantise(o, s, x, y, draw));
+  float2 pr;
+  const int q = level_of(pairs_s, hint_s, sf, fq.top, &pr);
+  if (mode == 2) {             // nearest colour: level q holds [midpoint below, midpoint above)
+    if (fminf(sf - pr.x, pr.y - sf) > fq.margin) return q;
+    return exact_quantise(og, s, x, y, draw);
+  }
+  if (q >= fq.top) return exact_quantise(og, s, x, y, draw);
   const float fr = __fdividef(sf - pr.x, pr.y - pr.x);
   float t;
-  if (o.dfamily == 0) t = 0.5f;
-  else if (o.dfamily == 1) t = ordf_s[(y & 7) * 8 + (x & 7)];
+  if (fam == 0) t = 0.5f;
+  else if (fam == 1) t = ordrow[x & 7];
   else t = (float)draw * (1.0f / 4294967295.0f);
-  if (fabsf(fr - t) > fq.margin) return q + (fr >= t ? 1 : 0);
-  return (int)(0.5 + exact_quantise(o, s, x, y, draw));
+  const float d = fr - t;
+  if (fabsf(d) > fq.margin) return q + (d >= 0.0f ? 1 : 0);
+  return exact_quantise(og, s, x, y, draw);
 }
 
-template <int S, int NCH>
+template <int S, int NCH, int R, int EPI>
 __global__ void __launch_bounds__(IWB_H_THREADS) iwb_hstream(const HStreamParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -288,16 +367,17 @@ __global__ void __launch_bounds__(IWB_H_THREADS) iwb_hstream(const HStreamParams
   int xb = xo0;                                          // first output still open at b0
   while (xb > 0 && p.sc.last[xb - 1] >= b0) xb--;
   const int nout = xo1 - xb;
+  constexpr int NV = NCH * R;                            // samples per thread and column
   double *w_s = (double *)smem_raw;                                        // [nb][S]
-  double *scr_all = w_s + (size_t)nb * S;                                  // [warps][S][NCH][32] parked samples
-  double *scr = scr_all + (size_t)warp * S * NCH * 32;
-  float2 *pairs_s = (float2 *)(scr_all + (size_t)IWB_H_WARPS * S * NCH * 32);   // [NCH][256]
+  double *scr_all = w_s + (size_t)nb * S;                                  // [warps][S][NV][32] parked samples
+  double *scr = scr_all + (size_t)warp * S * NV * 32;
+  float2 *pairs_s = (float2 *)(scr_all + (size_t)IWB_H_WARPS * S * NV * 32);    // [NCH][256]
   float *ordf_s = (float *)(pairs_s + NCH * 256);                          // [2][64]
-  float *ring = ordf_s + 128;                                              // [RING_D][NCH][threads]
-  int *last_s = (int *)(ring + IWB_RING_D * NCH * IWB_H_THREADS);          // [nout]
+  float *ring = ordf_s + 128;                                              // [RING_D][NV][threads]
+  int *last_s = (int *)(ring + IWB_RING_D * NV * IWB_H_THREADS);           // [nout]
   uint16_t *hint_s = (uint16_t *)(last_s + nout);                          // [NCH][1026]
   unsigned char *ost_all = (unsigned char *)(hint_s + NCH * 1026 + ((NCH * 1026) & 1));
-  unsigned char *ost = ost_all + (size_t)warp * 32 * IWB_OSTAGE_PITCH;
+  unsigned char *ost = ost_all + (size_t)warp * 32 * R * IWB_OSTAGE_PITCH; // [32*R rows][pitch]
 
   for (int i = threadIdx.x; i < nb * S; i += blockDim.x) w_s[i] = p.sc.w[(size_t)b0 * S + i];
   for (int i = threadIdx.x; i < nout; i += blockDim.x) last_s[i] = p.sc.last[xb + i] - b0;
@@ -322,54 +402,74 @@ __global__ void __launch_bounds__(IWB_H_THREADS) iwb_hstream(const HStreamParams
   }
   __syncthreads();
 
-  const int jb = p.row_lo + (blockIdx.y * IWB_H_WARPS + warp) * 32;   // first row of this warp
+  const int jb = p.row_lo + (blockIdx.y * IWB_H_WARPS + warp) * 32 * R;  // first row of this warp
   if (jb >= p.row_hi) return;
-  const int y = jb + lane;
-  const bool row_ok = y < p.row_hi;
+  int yr[R];
+  bool okr[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) { yr[r] = jb + r * 32 + lane; okr[r] = yr[r] < p.row_hi; }
 
-  double acc[S][NCH];
+  double acc[S][NV];
 #pragma unroll
   for (int s = 0; s < S; s++)
 #pragma unroll
-    for (int c = 0; c < NCH; c++) acc[s][c] = 0.0;
+    for (int v = 0; v < NV; v++) acc[s][v] = 0.0;
 
-  // random dither: this thread's draws are consecutive along its row, one per output pixel and channel
-  uint64_t rng[NCH];
+  // random dither: this thread's draws are consecutive along each of its rows, one per output pixel and channel
+  uint64_t rng[NV];
 #pragma unroll
-  for (int c = 0; c < NCH; c++) {
-    rng[c] = 0;
-    if (p.ch[c].dfamily == 3 && row_ok) {
+  for (int v = 0; v < NV; v++) {
+    const int c = v % NCH, r = v / NCH;
+    rng[v] = 0;
+    if (p.ch[c].dfamily == 3 && okr[r]) {
       uint64_t t = p.ch[c].prng_t1;
-      const uint64_t n = (uint64_t)y * (uint64_t)p.out_w + (uint64_t)xo0;
+      const uint64_t n = (uint64_t)yr[r] * (uint64_t)p.out_w + (uint64_t)xo0;
       if (n) { if (t >= IWB_PRNG_P) t -= IWB_PRNG_P; t = iwb_prng_jump(t, n, p.jump); }
-      rng[c] = t;
+      rng[v] = t;
     }
   }
+  const float *ordrow[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) ordrow[r] = ordf_s + (p.ch[0].dsubtype == 1 ? 64 : 0) + (yr[r] & 7) * 8;
 
-  // per-thread ring of intermediate samples: column b0+i, channel c, this thread's row
+  // per-thread ring of intermediate samples: column b0+i, channel c, row r of this thread
   float *myring = ring + threadIdx.x;
-  const float *colp = p.interT + (size_t)b0 * NCH * p.pitch_j + (size_t)(y - p.row_lo);
-  if (!row_ok) {
+  const float *gnext[R];
 #pragma unroll
-    for (int d = 0; d < IWB_RING_D * NCH; d++) myring[d * IWB_H_THREADS] = 0.0f;
-  }
-  auto issue = [&](int col) {
-    if (row_ok && col < nb) {
+  for (int r = 0; r < R; r++) gnext[r] = p.interT + (size_t)b0 * NCH * p.pitch_j + (size_t)(yr[r] - p.row_lo);
 #pragma unroll
-      for (int c = 0; c < NCH; c++)
-        cp_async4(myring + ((col % IWB_RING_D) * NCH + c) * IWB_H_THREADS, colp + ((size_t)col * NCH + c) * p.pitch_j);
+  for (int r = 0; r < R; r++)
+    if (!okr[r]) {
+#pragma unroll
+      for (int d = 0; d < IWB_RING_D; d++)
+#pragma unroll
+        for (int c = 0; c < NCH; c++) myring[(d * NV + r * NCH + c) * IWB_H_THREADS] = 0.0f;
     }
+  int requested = 0;
+  auto request = [&]() {
+    if (requested < nb) {
+      float *slot = myring + (requested % IWB_RING_D) * NV * IWB_H_THREADS;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        if (okr[r]) {
+#pragma unroll
+          for (int c = 0; c < NCH; c++) cp_async4(slot + (r * NCH + c) * IWB_H_THREADS, gnext[r] + (size_t)c * p.pitch_j);
+        }
+        gnext[r] += (size_t)NCH * p.pitch_j;
+      }
+    }
+    requested++;
     cp_async_commit();
   };
 #pragma unroll
-  for (int d = 0; d < IWB_RING_D - 1; d++) issue(d);
+  for (int d = 0; d < IWB_RING_D - 1; d++) request();
 
   int staged_from = xo0;        // first output pixel currently held in the staging tile
   const int px_per_flush = 128 / NCH;
-  auto flush = [&](int upto) {  // write staged pixels [staged_from, upto) of all 32 rows, coalesced per row
+  auto flush = [&](int upto) {  // write staged pixels [staged_from, upto) of this warp's rows, coalesced per row
     const int nbytes = (upto - staged_from) * NCH;
     __syncwarp();
-    for (int k = 0; k < 32; k++) {
+    for (int k = 0; k < 32 * R; k++) {
       const int yy = jb + k;
       if (yy >= p.row_hi) break;
       uint8_t *dst = p.out.pix + (size_t)(yy - p.out.row_origin) * p.out.bpr + (size_t)staged_from * NCH;
@@ -380,21 +480,54 @@ __global__ void __launch_bounds__(IWB_H_THREADS) iwb_hstream(const HStreamParams
   };
 
   int i = 0;                    // next input column (relative to b0)
-  auto col_step = [&]() {
-    issue(i + IWB_RING_D - 1);
+  int fetched = 0;
+  const double *wr = w_s;
+  auto fetch = [&](double (&v)[NV]) {   // one column ahead of the arithmetic (see the vertical kernel)
+    request();
     cp_async_wait<IWB_RING_D - 1>();
-    double v[NCH];
+    const float *slot = myring + (fetched % IWB_RING_D) * NV * IWB_H_THREADS;
 #pragma unroll
-    for (int c = 0; c < NCH; c++) v[c] = (double)myring[((i % IWB_RING_D) * NCH + c) * IWB_H_THREADS];
-    const double *wr = w_s + (size_t)i * S;
+    for (int q = 0; q < NV; q++) v[q] = (double)slot[q * IWB_H_THREADS];
+    fetched++;
+  };
+  double vcur[NV];
+  if (IWB_H_PIPE) fetch(vcur);
+  auto col_step = [&]() {
+    double vnext[NV];
+    if (IWB_H_PIPE) fetch(vnext);
+    else fetch(vcur);
 #pragma unroll
     for (int s = 0; s < S; s++) {
       const double w = wr[s];
 #pragma unroll
-      for (int c = 0; c < NCH; c++) acc[s][c] = __dadd_rn(acc[s][c], __dmul_rn(v[c], w));
+      for (int q = 0; q < NV; q++) acc[s][q] = __dadd_rn(acc[s][q], __dmul_rn(vcur[q], w));
     }
+    if (IWB_H_PIPE) {
+#pragma unroll
+      for (int q = 0; q < NV; q++) vcur[q] = vnext[q];
+    }
+    wr += S;
     i++;
   };
+
+  // quantise one finished pixel (this thread's R rows x NCH channels) and stage its bytes
+  unsigned char *ost_t = ost + lane * IWB_OSTAGE_PITCH;
+  auto emit = [&](const double *a, int astride, int xo) {
+    if (xo - staged_from >= px_per_flush) flush(xo);
+    unsigned char *dstb = ost_t + (xo - staged_from) * NCH;
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+      const int c = q % NCH, r = q / NCH;
+      const DevChanOut &o = p.ch[c];
+      uint32_t draw = 0;
+      if (EPI == 4 || (EPI == 0 && o.dfamily == 3)) { draw = iwb_prng_draw_of(rng[q]); rng[q] = iwb_prng_step(rng[q]); }
+      const float *orow = (EPI == 3) ? ordrow[r] : ordf_s + (o.dsubtype == 1 ? 64 : 0) + (yr[r] & 7) * 8;
+      const int code = quantise8_fast<EPI>(o, p.ch_g + c, p.fq[c], pairs_s + c * 256, hint_s + c * 1026, orow,
+                                           a[q * astride], xo, yr[r], draw);
+      dstb[r * 32 * IWB_OSTAGE_PITCH + c] = (uint8_t)code;
+    }
+  };
+  constexpr bool PARK = S > 8;   // many slots: one out-of-line copy of the epilogue instead of S inlined ones
 
   for (int og = xb - (xb % S); og < xo1; og += S) {
 #pragma unroll
@@ -403,26 +536,22 @@ __global__ void __launch_bounds__(IWB_H_THREADS) iwb_hstream(const HStreamParams
       if (o >= xb && o < xo1) {                            // warp-uniform
         const int iend = last_s[o - xb];
         while (i <= iend) col_step();
+        if (PARK) {
 #pragma unroll
-        for (int c = 0; c < NCH; c++) { scr[(k * NCH + c) * 32 + lane] = acc[k][c]; acc[k][c] = 0.0; }
+          for (int q = 0; q < NV; q++) scr[(k * NV + q) * 32 + lane] = acc[k][q];
+        } else if (o >= xo0) {
+          emit(&acc[k][0], 1, o);
+        }
+#pragma unroll
+        for (int q = 0; q < NV; q++) acc[k][q] = 0.0;
       }
     }
-    // epilogue for the outputs of this cycle, in increasing order (each thread reads back only its own values)
+    if (PARK) {   // epilogue for the outputs of this cycle, in increasing order (own values only: no barrier)
 #pragma unroll 1
-    for (int k = 0; k < S; k++) {
-      const int xo = og + k;
-      if (xo < xo0 || xo >= xo1) continue;
-      if (xo - staged_from >= px_per_flush) flush(xo);
-#pragma unroll
-      for (int c = 0; c < NCH; c++) {
-        double a = scr[(k * NCH + c) * 32 + lane];
-        if (p.intclamp) a = a < 0.0 ? 0.0 : (a > 1.0 ? 1.0 : a);
-        const DevChanOut &o = p.ch[c];
-        uint32_t draw = 0;
-        if (o.dfamily == 3) { draw = iwb_prng_draw_of(rng[c]); rng[c] = iwb_prng_step(rng[c]); }
-        const int code = quantise8_fast(o, p.fq[c], pairs_s + c * 256, hint_s + c * 1026, ordf_s + (o.dsubtype == 1 ? 64 : 0),
-                                        a, xo, y, draw);
-        ost[lane * IWB_OSTAGE_PITCH + (xo - staged_from) * NCH + o.out_ch] = (uint8_t)code;
+      for (int k = 0; k < S; k++) {
+        const int xo = og + k;
+        if (xo < xo0 || xo >= xo1) continue;
+        emit(scr + (size_t)k * NV * 32 + lane, 32, xo);
       }
     }
   }

@@ -433,8 +433,8 @@ bool upload_sched(iwb200_job *job, const HostSched &hs, int n_in, int n_out, Axi
 
 template <int S, int NC>
 void launch_v(const VStreamParams &p, dim3 grid, size_t smem, iwb_stream st) {
-  // the cp.async ring moves 4 bytes per thread and row: needs NC == 4 and 4-byte aligned rows
-  const bool ring = NC == 4 && (p.bpr % 4 == 0) && (((uintptr_t)p.src + p.x0_bytes) % 4 == 0) && (p.ncols % 4 == 0);
+  // the cp.async ring moves NC bytes per thread and row: needs NC in {4,8} and NC-byte aligned rows
+  const bool ring = NC >= 4 && (p.bpr % NC == 0) && (((uintptr_t)p.src + p.x0_bytes) % NC == 0) && (p.ncols % NC == 0);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(iwb_vstream<S, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -444,67 +444,96 @@ void launch_v(const VStreamParams &p, dim3 grid, size_t smem, iwb_stream st) {
   if (ring) iwb_vstream<S, NC, true><<<grid, IWB_V_THREADS, smem, st>>>(p);
   else iwb_vstream<S, NC, false><<<grid, IWB_V_THREADS, smem, st>>>(p);
 }
-template <int S, int NCH>
+template <int S, int NCH, int R, int EPI>
 void launch_h(const HStreamParams &p, dim3 grid, size_t smem, iwb_stream st) {
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(iwb_hstream<S, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-  iwb_hstream<S, NCH><<<grid, 32 * IWB_H_WARPS, smem, st>>>(p);
+  if (!attr) { cudaFuncSetAttribute(iwb_hstream<S, NCH, R, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  iwb_hstream<S, NCH, R, EPI><<<grid, IWB_H_THREADS, smem, st>>>(p);
 }
 
-template <int NC>
-bool dispatch_v_nc(int S, const VStreamParams &p, dim3 g, size_t sm, iwb_stream st) {
-  switch (S) {
-    case 2: launch_v<2, NC>(p, g, sm, st); return true;
-    case 3: launch_v<3, NC>(p, g, sm, st); return true;
-    case 4: launch_v<4, NC>(p, g, sm, st); return true;
-    case 5: launch_v<5, NC>(p, g, sm, st); return true;
-    case 6: launch_v<6, NC>(p, g, sm, st); return true;
-    case 8: launch_v<8, NC>(p, g, sm, st); return true;
-  }
+#ifdef IWB_QUICK   // tuning builds: only the variants the headline configuration uses
+bool dispatch_v(int S, int NC, const VStreamParams &p, dim3 g, size_t sm, iwb_stream st) {
+  if (S == 6 && NC == 4) { launch_v<6, 4>(p, g, sm, st); return true; }
   return false;
 }
+bool dispatch_h(int S, int NCH, int EPI, const HStreamParams &p, dim3 g, size_t sm, iwb_stream st) {
+  if (S == 6 && NCH == 3 && EPI == 3) { launch_h<6, 3, 1, 3>(p, g, sm, st); return true; }
+  return false;
+}
+int h_rows_per_thread(int, int) { return 1; }
+#else
 bool dispatch_v(int S, int NC, const VStreamParams &p, dim3 g, size_t sm, iwb_stream st) {
-  if (NC == 4) return dispatch_v_nc<4>(S, p, g, sm, st);
-  if (NC == 2) {
+  if (NC == 8) {
+    switch (S) {
+      case 2: launch_v<2, 8>(p, g, sm, st); return true;
+      case 3: launch_v<3, 8>(p, g, sm, st); return true;
+      case 4: launch_v<4, 8>(p, g, sm, st); return true;
+      case 5: launch_v<5, 8>(p, g, sm, st); return true;
+      case 6: launch_v<6, 8>(p, g, sm, st); return true;
+    }
+  } else if (NC == 4) {
+    switch (S) {
+      case 2: launch_v<2, 4>(p, g, sm, st); return true;
+      case 3: launch_v<3, 4>(p, g, sm, st); return true;
+      case 4: launch_v<4, 4>(p, g, sm, st); return true;
+      case 5: launch_v<5, 4>(p, g, sm, st); return true;
+      case 6: launch_v<6, 4>(p, g, sm, st); return true;
+      case 8: launch_v<8, 4>(p, g, sm, st); return true;
+    }
+  } else if (NC == 2) {
     if (S == 12) { launch_v<12, 2>(p, g, sm, st); return true; }
     if (S == 16) { launch_v<16, 2>(p, g, sm, st); return true; }
   }
   return false;
 }
-template <int NCH>
-bool dispatch_h_nch(int S, const HStreamParams &p, dim3 g, size_t sm, iwb_stream st) {
-  switch (S) {
-    case 2: launch_h<2, NCH>(p, g, sm, st); return true;
-    case 3: launch_h<3, NCH>(p, g, sm, st); return true;
-    case 4: launch_h<4, NCH>(p, g, sm, st); return true;
-    case 5: launch_h<5, NCH>(p, g, sm, st); return true;
-    case 6: launch_h<6, NCH>(p, g, sm, st); return true;
-    case 8: launch_h<8, NCH>(p, g, sm, st); return true;
-    case 12: launch_h<12, NCH>(p, g, sm, st); return true;
-    case 16: launch_h<16, NCH>(p, g, sm, st); return true;
+template <int NCH, int EPI>
+bool dispatch_h_s(int S, const HStreamParams &p, dim3 g, size_t sm, iwb_stream st) {
+  switch (S) {   // one row per thread: two rows per thread measured slower (fewer resident warps)
+    case 2: launch_h<2, NCH, 1, EPI>(p, g, sm, st); return true;
+    case 3: launch_h<3, NCH, 1, EPI>(p, g, sm, st); return true;
+    case 4: launch_h<4, NCH, 1, EPI>(p, g, sm, st); return true;
+    case 5: launch_h<5, NCH, 1, EPI>(p, g, sm, st); return true;
+    case 6: launch_h<6, NCH, 1, EPI>(p, g, sm, st); return true;
+    case 8: launch_h<8, NCH, 1, EPI>(p, g, sm, st); return true;
+    case 12: launch_h<12, NCH, 1, EPI>(p, g, sm, st); return true;
+    case 16: launch_h<16, NCH, 1, EPI>(p, g, sm, st); return true;
   }
   return false;
 }
-bool dispatch_h(int S, int NCH, const HStreamParams &p, dim3 g, size_t sm, iwb_stream st) {
-  if (NCH == 1) return dispatch_h_nch<1>(S, p, g, sm, st);
-  if (NCH == 3) return dispatch_h_nch<3>(S, p, g, sm, st);
+int h_rows_per_thread(int, int) { return 1; }  // must mirror dispatch_h_s
+template <int NCH>
+bool dispatch_h_e(int S, int EPI, const HStreamParams &p, dim3 g, size_t sm, iwb_stream st) {
+  switch (EPI) {
+    case 1: return dispatch_h_s<NCH, 1>(S, p, g, sm, st);
+    case 2: return dispatch_h_s<NCH, 2>(S, p, g, sm, st);
+    case 3: return dispatch_h_s<NCH, 3>(S, p, g, sm, st);
+    case 4: return dispatch_h_s<NCH, 4>(S, p, g, sm, st);
+  }
+  return dispatch_h_s<NCH, 0>(S, p, g, sm, st);
+}
+bool dispatch_h(int S, int NCH, int EPI, const HStreamParams &p, dim3 g, size_t sm, iwb_stream st) {
+  if (NCH == 1) return dispatch_h_e<1>(S, EPI, p, g, sm, st);
+  if (NCH == 3) return dispatch_h_e<3>(S, EPI, p, g, sm, st);
   return false;
 }
+#endif
 
 // nr/nb: input samples of the longest strip/segment; nout: outputs tracked (strip/segment + still-open predecessors)
 size_t v_smem_bytes(int nr, int S, int nout, int nc) {
-  return (size_t)256 * 16 * 8 + (size_t)nr * S * 8 + (size_t)((nout + 3) & ~3) * 4 + (size_t)IWB_RING_D * IWB_V_THREADS * 4 +
-         (size_t)8 * nc * IWB_V_THREADS * 4 + 16;
+  const int nw = nc >= 4 ? nc / 4 : 1, tb = IWB_V_TB;
+  return (size_t)256 * IWB_LUT_REP * 8 + (size_t)nr * S * 8 + (size_t)((nout + 3) & ~3) * 4 +
+         (size_t)IWB_RING_D * IWB_V_THREADS * nw * 4 + (size_t)tb * nc * IWB_V_THREADS * 4 + 16;
 }
-size_t h_smem_bytes(int nb, int S, int nch, int nout) {
+size_t h_smem_bytes(int nb, int S, int nch, int nout, int R) {
+  const int nv = nch * R;
   size_t b = (size_t)nb * S * 8;
-  b += (size_t)IWB_H_WARPS * S * nch * 32 * 8;      // parked samples
+  b += (size_t)IWB_H_WARPS * S * nv * 32 * 8;       // parked samples
   b += (size_t)nch * 256 * 8;                       // float2 level bounds
   b += 128 * 4;                                     // ordered-dither thresholds
-  b += (size_t)IWB_RING_D * nch * IWB_H_THREADS * 4;
+  b += (size_t)IWB_RING_D * nv * IWB_H_THREADS * 4;
   b += (size_t)nout * 4;
   b += (size_t)(nch * 1026 + ((nch * 1026) & 1)) * 2;
-  b += (size_t)IWB_H_WARPS * 32 * IWB_OSTAGE_PITCH;
+  b += (size_t)IWB_H_WARPS * 32 * R * IWB_OSTAGE_PITCH;
   return b + 16;
 }
 
@@ -521,7 +550,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
   if (ctx->in_type_logical != ctx->img1.imgtype) return;
   if (job->nproc != nch || ctx->out_nch != nch || job->has_alpha) return;
   if (ctx->img2.sampletype != IW_SAMPLETYPE_UINT || ctx->img2.bit_depth != 8) return;
-  if (job->any_errdiff) return;
+  if (job->any_errdiff || ctx->intclamp) return;
   if (ctx->axis[0].per_channel_tables || ctx->axis[1].per_channel_tables) return;
   for (int p = 0; p < nch; p++) {
     const iwb_mid_channel &mc = ctx->mid_ci[job->mid_index[p]];
@@ -532,7 +561,13 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
   if (!build_sched(job->vtab[0], 16, &hv)) return;
   if (!build_sched(job->htab[0], 16, &hh)) return;
   if (hh.S * nch > 48) return;
-  f->NC = hv.S <= 8 ? 4 : 2;
+  {
+    // 8 byte columns per thread when the rows allow 8-byte requests and the accumulators still fit
+    const bool al8 = (ctx->img1.bpr % 8 == 0) && (((size_t)ctx->in_x0 * nch) % 8 == 0) && ((job->in_w * nch) % 8 == 0);
+    f->NC = hv.S <= 8 ? 4 : 2;   // (8 columns per thread measured slower: fewer resident warps)
+    (void)al8;
+    if (const char *o = iwb_option(ctx, "cuda:nc")) { int v = atoi(o); if ((v == 4 && hv.S <= 8) || (v == 8 && hv.S <= 6)) f->NC = v; }
+  }
   f->nch = nch;
   f->SV = hv.S;
   f->SH = hh.S;
@@ -575,7 +610,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
   }
   while (true) {
     f->h_nb_max = longest_any(hh.first, hh.last, f->seg);
-    f->h_smem = h_smem_bytes(f->h_nb_max, f->SH, nch, f->seg + f->SH);
+    f->h_smem = h_smem_bytes(f->h_nb_max, f->SH, nch, f->seg + f->SH, h_rows_per_thread(f->SH, nch));
     if (f->h_smem <= 160 * 1024 || f->seg <= 8) break;
     f->seg = (f->seg / 2) & ~3;
   }
@@ -630,6 +665,22 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
     q.hint = job->upload(hint.data(), hint.size());
     if (!q.pairs || !q.hint) return;
   }
+  // epilogue specialisation: all channels in the same fast mode and dither, else the run-time generic one
+  {
+    bool same = true;
+    for (int p = 1; p < nch; p++)
+      if (f->fq[p].mode != f->fq[0].mode || job->cout[p].dfamily != job->cout[0].dfamily ||
+          job->cout[p].dsubtype != job->cout[0].dsubtype) same = false;
+    f->epi = 0;
+    if (same && f->fq[0].mode == 2) f->epi = 2;
+    if (same && f->fq[0].mode == 1) f->epi = job->cout[0].dfamily == 0 ? 1 : (job->cout[0].dfamily == 1 ? 3 : 4);
+  }
+  {
+    DevChanOut four[4];
+    for (int p = 0; p < 4; p++) four[p] = job->cout[p < nch ? p : 0];
+    f->ch_g = job->upload(four, 4);
+    if (!f->ch_g) return;
+  }
   f->vfirst = hv.first;
   f->vlast = hv.last;
   f->enabled = 1;
@@ -657,12 +708,14 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
     }
     HStreamParams hp;
     hp.interT = f->interT; hp.pitch_j = f->pitch_j; hp.row_lo = c0; hp.row_hi = c1; hp.sc = f->sh; hp.seg = f->seg;
+    hp.ch_g = f->ch_g;
     hp.out = out; hp.intclamp = job->cm.intclamp; hp.out_w = out.width; hp.jump = job->d_jump;
     for (int p = 0; p < 4; p++) { hp.ch[p] = job->cout[p < nch ? p : 0]; hp.fq[p] = f->fq[p < nch ? p : 0]; }
-    dim3 gh((unsigned)((out.width + f->seg - 1) / f->seg), (unsigned)((c1 - c0 + 32 * IWB_H_WARPS - 1) / (32 * IWB_H_WARPS)));
+    const int rows_per_cta = 32 * IWB_H_WARPS * h_rows_per_thread(f->SH, nch);
+    dim3 gh((unsigned)((out.width + f->seg - 1) / f->seg), (unsigned)((c1 - c0 + rows_per_cta - 1) / rows_per_cta));
     {
       prof_scope ps(job, 1, stream);
-      if (!dispatch_h(f->SH, nch, hp, gh, f->h_smem, stream)) return fail(job, "fast path: no horizontal kernel variant");
+      if (!dispatch_h(f->SH, nch, f->epi, hp, gh, f->h_smem, stream)) return fail(job, "fast path: no horizontal kernel variant");
       g_launches++;
     }
     if (job->negate) {
