@@ -181,6 +181,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="context option name=value (tuning)")
+    ap.add_argument("--shard", default="images", choices=["images", "bands"],
+                    help="N>1: one image per GPU (weak scaling, default) or one image split into output-row bands "
+                         "gathered to rank 0 over NCCL (strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -256,11 +259,21 @@ def main():
     d_out = [torch.empty(out_bytes, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
     stream = torch.cuda.Stream()
 
+    from imageworsener_b200 import bands as _bands
+    band_mode = args.shard == "bands" and world > 1
+    r0, r1 = _bands.band_rows(info.out_height, rank, world) if band_mode else (0, info.out_height)
+    hmax = max(b - a for a, b in _bands.all_bands(info.out_height, world)) if band_mode else info.out_height
+    gathered = [torch.empty(hmax * info.out_bpr, dtype=torch.uint8, device="cuda") for _ in range(world)] \
+        if band_mode and rank == 0 else None
+
     def step(i):
-        ok = dll.iwb200_job_run_device(job, d_in[i % nbuf].data_ptr(), cfg.in_bpr, 0, d_out[i % nbuf].data_ptr(),
-                                       info.out_bpr, 0, info.out_height, stream.cuda_stream)
+        out_t = d_out[i % nbuf]
+        ok = dll.iwb200_job_run_device(job, d_in[i % nbuf].data_ptr(), cfg.in_bpr, 0, out_t.data_ptr(),
+                                       info.out_bpr, r0, r1, stream.cuda_stream)
         if not ok:
             raise SystemExit("run_device failed: " + dll.iwb200_job_last_error(job).decode())
+        if band_mode:   # the only exchange of the path: output bands -> rank 0 (NCCL over NVLink)
+            dist.gather(out_t[: hmax * info.out_bpr], gather_list=gathered, dst=0)
 
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
@@ -291,7 +304,7 @@ def main():
         stream.synchronize()
     clocks = sampler.stop()
     ms_per_step = ms_total / args.steps
-    value = world * cfg.out_mpix / (ms_per_step / 1000.0)
+    value = (1 if band_mode else world) * cfg.out_mpix / (ms_per_step / 1000.0)
 
     # ---------------- per-kernel device time -> roofline of the dominant kernel ------------------------
     dll.iwb200_job_set_profiling(job, 1)
@@ -360,11 +373,12 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if band_mode else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"{args.config}: {cfg.description}", "in": [cfg.in_w, cfg.in_h],
                            "out": [cfg.out_w, cfg.out_h], "images_per_step_per_gpu": 1,
-                           "sharding": "one image per GPU, no data-path collective" if world > 1 else "single GPU",
+                           "sharding": ("one image split into output-row bands, gathered to rank 0 with NCCL" if band_mode else
+                                        "one image per GPU, no data-path collective") if world > 1 else "single GPU",
                            "l2_defeat": f"{nbuf} rotating input/output buffer sets ({nbuf * (cfg.in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2)",
                            "fused_kernel": bool(info.uses_fused_kernel)},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,

@@ -143,6 +143,10 @@ int iw_process_image(struct iw_context *ctx) {
   return 1;
 }
 
+void iwb200_detach_input_image(struct iw_context *ctx) {
+  if (ctx) ctx->img1.pixels = nullptr;
+}
+
 int iwb200_get_band(struct iw_context *ctx, int *r0, int *r1) {
   if (!ctx) return 0;
   *r0 = ctx->band_row0;

@@ -333,6 +333,10 @@ void iwb200_job_reset_stats(iwb200_job *job);
 void iwb200_synth_xorshift(uint8_t *buf, size_t n, uint64_t seed);
 uint64_t iwb200_fnv1a64(const uint8_t *buf, size_t n);
 
+/* Forget the input pixels without freeing them: for callers that lend a buffer they own (see INTEGRATION.md
+ * section 2) instead of transferring ownership as iw_set_input_image() normally does. */
+void iwb200_detach_input_image(struct iw_context *ctx);
+
 /* After iw_process_image() with option "cuda:band" set: which output rows the output image holds. */
 int iwb200_get_band(struct iw_context *ctx, int *out_row0, int *out_row1);
 
