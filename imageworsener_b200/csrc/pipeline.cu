@@ -215,6 +215,10 @@ struct iwb200_job {
   std::vector<timed> pending;
   int stat_n[6] = {0, 0, 0, 0, 0, 0};
   double stat_ms[6] = {0, 0, 0, 0, 0, 0};
+  std::string key;            // plan-cache key (empty: not cacheable)
+  int reused = 0, used_external_stream = 0;
+  void *streams[3] = {nullptr, nullptr, nullptr};   // run_host pipeline: copy-in, compute, copy-out
+  std::vector<void *> events;
   // staging for run_host
   void *d_in = nullptr; size_t d_in_bytes = 0;
   void *d_out = nullptr; size_t d_out_bytes = 0;
@@ -731,6 +735,75 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
 }
 #endif  // !IWB_EMU
 
+static void job_free(iwb200_job *job) {
+  if (!job) return;
+#if !defined(IWB_EMU)
+  for (int k = 0; k < 3; k++) if (job->streams[k]) cudaStreamDestroy((cudaStream_t)job->streams[k]);
+  for (void *e : job->events) cudaEventDestroy((cudaEvent_t)e);
+#endif
+  for (void *p : job->allocs) dev_free(p);
+  dev_free(job->d_in);
+  dev_free(job->d_out);
+  delete job;
+}
+
+// ---- plan cache.  A built job (device tables, schedules, scratch, staging buffers, streams) depends only on the
+// settings serialised by plan_key(); finished jobs are parked here and handed to the next context with the
+// same key, so a batch of same-shaped images builds its plan once.  Disable with IWB200_PLAN_CACHE=0.
+static std::mutex g_pool_mu;
+static std::vector<iwb200_job *> g_pool;   // idle jobs, most recently used last
+static const size_t kPoolMax = 8;
+
+template <class T>
+static void key_put(std::string &k, const T &v) { k.append(reinterpret_cast<const char *>(&v), sizeof(T)); }
+
+static std::string plan_key(const iw_context *c, int device) {
+  std::string k;
+  key_put(k, device);
+  key_put(k, c->img1.imgtype); key_put(k, c->img1.bit_depth); key_put(k, c->img1.sampletype);
+  key_put(k, c->img1.width); key_put(k, c->img1.height); key_put(k, c->img1.bpr); key_put(k, c->img1.orient_transform);
+  key_put(k, c->img1cs); key_put(k, c->img2cs);
+  key_put(k, c->in_x0); key_put(k, c->in_y0); key_put(k, c->in_w); key_put(k, c->in_h);
+  key_put(k, c->in_type_logical); key_put(k, c->in_nch_phys); key_put(k, c->in_nch_logical); key_put(k, c->in_alpha_index);
+  for (int i = 0; i < 4; i++) { key_put(k, c->in_ci[i].channeltype); key_put(k, c->in_ci[i].slow_path); key_put(k, c->in_ci[i].maxcode); }
+  key_put(k, c->mid_type); key_put(k, c->mid_nch); key_put(k, c->mid_alpha_index);
+  for (int i = 0; i < 4; i++) {
+    const iwb_mid_channel &m = c->mid_ci[i];
+    key_put(k, m.channeltype); key_put(k, m.to_gray); key_put(k, m.in_channel); key_put(k, m.out_channel);
+    key_put(k, m.early_bkgd); key_put(k, m.premultiplied);
+  }
+  key_put(k, c->img2.imgtype); key_put(k, c->img2.bit_depth); key_put(k, c->img2.sampletype);
+  key_put(k, c->img2.width); key_put(k, c->img2.height); key_put(k, c->out_nch);
+  for (int i = 0; i < 4; i++) {
+    const iwb_out_channel &o = c->out_ci[i];
+    key_put(k, o.channeltype); key_put(k, o.dither_family); key_put(k, o.dither_subtype); key_put(k, o.color_count);
+    key_put(k, o.maxcode); key_put(k, o.bkgd1); key_put(k, o.bkgd2);
+  }
+  for (int d = 0; d < 2; d++) {
+    const iwb_axis_request &a = c->axis[d];
+    key_put(k, a.family); key_put(k, a.edge_policy); key_put(k, a.use_offset); key_put(k, a.per_channel_tables);
+    key_put(k, a.param1); key_put(k, a.param2); key_put(k, a.blur); key_put(k, a.out_true_size); key_put(k, a.translate);
+    for (int j = 0; j < 3; j++) key_put(k, a.channel_offset[j]);
+  }
+  key_put(k, c->grayscale_formula); for (int j = 0; j < 3; j++) key_put(k, c->gray_w[j]);
+  key_put(k, c->no_gamma); key_put(k, c->intclamp); key_put(k, c->random_seed); key_put(k, c->negate_target);
+  key_put(k, c->apply_bkgd); key_put(k, c->bkgd_strategy); key_put(k, c->bkgd_checkerboard); key_put(k, c->bkgd_source);
+  key_put(k, c->bkgd1alpha); key_put(k, c->bkgd2alpha); key_put(k, c->check_size);
+  key_put(k, c->check_origin[0]); key_put(k, c->check_origin[1]);
+  key_put(k, c->disable_out_tables); key_put(k, c->reduced_out_maxcode); key_put(k, c->output_profile);
+  key_put(k, c->in_label_inputcs.c[3]); key_put(k, c->req_bkgd.c[3]); key_put(k, c->req_bkgd2.c[3]);
+  for (const struct iwb_option &o : c->options)
+    if (o.name.compare(0, 5, "cuda:") == 0 && o.name != "cuda:band") { k += o.name; k += '='; k += o.val; k += ';'; }
+  return k;
+}
+
+static bool pool_enabled() {
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("IWB200_PLAN_CACHE"); on = !(e && e[0] == '0'); }
+  return on != 0;
+}
+
+
 extern "C" {
 
 const char *iwb200_version(void) {
@@ -745,10 +818,21 @@ const char *iwb200_job_last_error(const iwb200_job *job) { return job ? job->err
 
 void iwb200_job_destroy(iwb200_job *job) {
   if (!job) return;
-  for (void *p : job->allocs) dev_free(p);
-  dev_free(job->d_in);
-  dev_free(job->d_out);
-  delete job;
+  if (pool_enabled() && job->err.empty() && !job->key.empty()) {
+#if !defined(IWB_EMU)
+    if (job->used_external_stream) { cudaSetDevice(job->device); cudaDeviceSynchronize(); job->used_external_stream = 0; }
+#endif
+    job->ctx = nullptr;
+    iwb200_job *evict = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(g_pool_mu);
+      g_pool.push_back(job);
+      if (g_pool.size() > kPoolMax) { evict = g_pool.front(); g_pool.erase(g_pool.begin()); }
+    }
+    job_free(evict);
+    return;
+  }
+  job_free(job);
 }
 
 // The context must have been through iwb_prepare() (iw_process_image does that; standalone callers use
@@ -982,12 +1066,26 @@ iwb200_job *iwb200_job_create(struct iw_context *ctx, int device) {
     ctx->use_count++;
     if (!iwb_prepare(ctx)) return nullptr;
   }
+  std::string key = plan_key(ctx, device);
+  if (pool_enabled()) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = g_pool.size(); i-- > 0;)
+      if (g_pool[i]->key == key) {
+        iwb200_job *job = g_pool[i];
+        g_pool.erase(g_pool.begin() + i);
+        job->ctx = ctx;
+        job->errdiff_next_row = 0;
+        job->reused = 1;
+        return job;
+      }
+  }
   iwb200_job *job = job_build(ctx, device);
   if (!job->err.empty()) {
     iw_set_errorf(ctx, "%s", job->err.c_str());
-    iwb200_job_destroy(job);
+    job_free(job);
     return nullptr;
   }
+  job->key = std::move(key);
   return job;
 }
 
@@ -1020,6 +1118,7 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
   if (!job) return 0;
   iwb_stream stream = (iwb_stream)stream_;
   if (r0 < 0 || r1 > job->out.height || r0 >= r1) return fail(job, "invalid output row band");
+  if (stream_ && stream_ != job->streams[1]) job->used_external_stream = 1;
   if (job->any_errdiff && r0 != job->errdiff_next_row && r0 != 0)
     return fail(job, "error-diffusion dither must be processed in row order from row 0");
 #if !defined(IWB_EMU)
@@ -1151,34 +1250,66 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
   if (job->d_out_bytes < out_bytes) { dev_free(job->d_out); job->d_out = dev_alloc(out_bytes, job->err); job->d_out_bytes = out_bytes; }
   if (!job->d_in || !job->d_out) { job->d_in_bytes = job->d_out_bytes = 0; return 0; }
   iwb_timings &tm = job->ctx->timings;
-#if !defined(IWB_EMU)
-  cudaEvent_t e[4];
-  for (auto &x : e) cudaEventCreate(&x);
-  cudaEventRecord(e[0], 0);
-#endif
-  if (!dev_h2d(job->d_in, (const uint8_t *)h_in + (size_t)first * in_bpr, in_bytes, 0, job->err)) return 0;
-#if !defined(IWB_EMU)
-  cudaEventRecord(e[1], 0);
-#endif
-  if (!iwb200_job_run_device(job, job->d_in, in_bpr, first, job->d_out, out_bpr, r0, r1, 0)) return 0;
-#if !defined(IWB_EMU)
-  cudaEventRecord(e[2], 0);
-#endif
-  if (!dev_d2h(h_out, job->d_out, out_bytes, 0, job->err)) return 0;
-#if !defined(IWB_EMU)
-  cudaEventRecord(e[3], 0);
-#endif
-  if (!dev_sync(0, job->err)) return 0;
-#if !defined(IWB_EMU)
-  float ms = 0;
-  cudaEventElapsedTime(&ms, e[0], e[1]); tm.h2d_ms = ms;
-  cudaEventElapsedTime(&ms, e[1], e[2]); tm.kernel_ms = ms;
-  cudaEventElapsedTime(&ms, e[2], e[3]); tm.d2h_ms = ms;
-  for (auto &x : e) cudaEventDestroy(x);
-#else
+#if defined(IWB_EMU)
   (void)tm;
-#endif
+  if (!dev_h2d(job->d_in, (const uint8_t *)h_in + (size_t)first * in_bpr, in_bytes, 0, job->err)) return 0;
+  if (!iwb200_job_run_device(job, job->d_in, in_bpr, first, job->d_out, out_bpr, r0, r1, 0)) return 0;
+  if (!dev_d2h(h_out, job->d_out, out_bytes, 0, job->err)) return 0;
   return 1;
+#else
+  // Software pipeline over output-row sub-bands: while sub-band k computes, the input rows of k+1 arrive and the
+  // output rows of k-1 leave (three streams, page-locked host buffers).  The kernels take a fraction of the PCIe
+  // time, so the call costs about one H2D of the image.  Sequential (error-diffusion) jobs use one sub-band.
+  cudaSetDevice(job->device);
+  if (!job->streams[0])
+    for (int k = 0; k < 3; k++) { cudaStream_t st; cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking); job->streams[k] = st; }
+  cudaStream_t s_in = (cudaStream_t)job->streams[0], s_k = (cudaStream_t)job->streams[1], s_out = (cudaStream_t)job->streams[2];
+  int nsub = 1;
+  const bool transposed = (job->in.orient & 4) != 0, flipped = (job->in.orient & 2) != 0;
+  if (job->info.bandable && !transposed && !flipped && in_bytes >= ((size_t)8 << 20)) nsub = (int)std::min<size_t>(6, (size_t)(r1 - r0) / 256);
+  if (const char *o = iwb_option(job->ctx, "cuda:pipeline")) nsub = std::max(1, atoi(o));
+  nsub = std::max(1, std::min(nsub, r1 - r0));
+  while ((int)job->events.size() < 2 * nsub + 2) { cudaEvent_t e; cudaEventCreate(&e); job->events.push_back(e); }
+  auto ev = [&](int i) { return (cudaEvent_t)job->events[i]; };
+  // the default stream may still be uploading this job's tables
+  cudaEventRecord(ev(2 * nsub), 0);
+  cudaStreamWaitEvent(s_k, ev(2 * nsub), 0);
+  cudaEventRecord(ev(2 * nsub + 1), s_in);       // timing origin
+  int copied_to = first - 1;                     // last physical input row already requested
+  bool ok = true;
+  for (int k = 0; k < nsub && ok; k++) {
+    const int b0 = r0 + (int)(((long long)(r1 - r0) * k) / nsub), b1 = r0 + (int)(((long long)(r1 - r0) * (k + 1)) / nsub);
+    int f, l;
+    iwb200_job_band_input_rows(job, b0, b1, &f, &l);
+    l = std::min(l, last);
+    if (nsub == 1) l = last;
+    if (l > copied_to) {
+      const size_t off = (size_t)(copied_to + 1 - first) * in_bpr, n = (size_t)(l - copied_to) * in_bpr;
+      ok = dev_h2d((uint8_t *)job->d_in + off, (const uint8_t *)h_in + (size_t)(copied_to + 1) * in_bpr, n, s_in, job->err);
+      copied_to = l;
+    }
+    cudaEventRecord(ev(2 * k), s_in);
+    cudaStreamWaitEvent(s_k, ev(2 * k), 0);
+    ok = ok && iwb200_job_run_device(job, job->d_in, in_bpr, first, (uint8_t *)job->d_out + (size_t)(b0 - r0) * out_bpr, out_bpr,
+                                     b0, b1, s_k);
+    cudaEventRecord(ev(2 * k + 1), s_k);
+    cudaStreamWaitEvent(s_out, ev(2 * k + 1), 0);
+    ok = ok && dev_d2h((uint8_t *)h_out + (size_t)(b0 - r0) * out_bpr, (uint8_t *)job->d_out + (size_t)(b0 - r0) * out_bpr,
+                       (size_t)(b1 - b0) * out_bpr, s_out, job->err);
+  }
+  if (!dev_sync(s_out, job->err)) return 0;
+  if (!dev_sync(s_k, job->err) || !dev_sync(s_in, job->err)) return 0;
+  if (!ok) return 0;
+  float ms = 0;
+  // with overlap the three phases are concurrent: report copy-in span, compute span after the last copy-in,
+  // and copy-out span after the last kernel
+  cudaEventElapsedTime(&ms, ev(2 * nsub + 1), ev(2 * (nsub - 1))); tm.h2d_ms = ms;
+  cudaEventElapsedTime(&ms, ev(2 * (nsub - 1)), ev(2 * (nsub - 1) + 1)); tm.kernel_ms = ms;
+  cudaEvent_t done; cudaEventCreate(&done); cudaEventRecord(done, s_out); cudaEventSynchronize(done);
+  cudaEventElapsedTime(&ms, ev(2 * (nsub - 1) + 1), done); tm.d2h_ms = ms;
+  cudaEventDestroy(done);
+  return 1;
+#endif
 }
 
 }  // extern "C"
