@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(IWB_V_THREADS, (NC >= 8 ? 3 : IWB_V_MINBLOCKS)
 // nearest-colour midpoint table; EPI = 0: anything else, decided per sample at run time.
 // ---------------------------------------------------------------------------------------------------------
 #ifndef IWB_H_WARPS
-#define IWB_H_WARPS 8
+#define IWB_H_WARPS 4
 #endif
 #define IWB_H_THREADS (32 * IWB_H_WARPS)
 #define IWB_OSTAGE_PITCH 132   // bytes per staging row (33 words: lane-private banks)
@@ -369,9 +369,10 @@ __global__ void __launch_bounds__(IWB_H_THREADS) iwb_hstream(const HStreamParams
   const int nout = xo1 - xb;
   constexpr int NV = NCH * R;                            // samples per thread and column
   double *w_s = (double *)smem_raw;                                        // [nb][S]
-  double *scr_all = w_s + (size_t)nb * S;                                  // [warps][S][NV][32] parked samples
-  double *scr = scr_all + (size_t)warp * S * NV * 32;
-  float2 *pairs_s = (float2 *)(scr_all + (size_t)IWB_H_WARPS * S * NV * 32);    // [NCH][256]
+  constexpr int NPARK = S > 8 ? S * NV * 32 : 0;                           // parked samples only when not inlined
+  double *scr_all = w_s + (size_t)nb * S;                                  // [warps][S][NV][32]
+  double *scr = scr_all + (size_t)warp * NPARK;
+  float2 *pairs_s = (float2 *)(scr_all + (size_t)IWB_H_WARPS * NPARK);     // [NCH][256]
   float *ordf_s = (float *)(pairs_s + NCH * 256);                          // [2][64]
   float *ring = ordf_s + 128;                                              // [RING_D][NV][threads]
   int *last_s = (int *)(ring + IWB_RING_D * NV * IWB_H_THREADS);           // [nout]

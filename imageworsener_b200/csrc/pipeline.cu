@@ -531,7 +531,7 @@ size_t v_smem_bytes(int nr, int S, int nout, int nc) {
 size_t h_smem_bytes(int nb, int S, int nch, int nout, int R) {
   const int nv = nch * R;
   size_t b = (size_t)nb * S * 8;
-  b += (size_t)IWB_H_WARPS * S * nv * 32 * 8;       // parked samples
+  if (S > 8) b += (size_t)IWB_H_WARPS * S * nv * 32 * 8;       // parked samples (inlined epilogue otherwise)
   b += (size_t)nch * 256 * 8;                       // float2 level bounds
   b += 128 * 4;                                     // ordered-dither thresholds
   b += (size_t)IWB_RING_D * nv * IWB_H_THREADS * 4;
