@@ -21,7 +21,8 @@ EMU_DIR = os.path.join(ROOT, "tests", "_emu")
 EMU_SO = os.path.join(EMU_DIR, "libimagew_emu.so")
 
 HOST_SOURCES = ["api.cpp", "plan.cpp", "weights.cpp", "tables.cpp", "process.cpp"]
-DEVICE_SOURCES = ["pipeline.cu"]
+DEVICE_SOURCES = ["pipeline.cu", "stream2.cu"]
+OBJ_DIR = os.path.join(HERE, "_obj")
 
 
 def _newer(target: str, deps: list[str]) -> bool:
@@ -54,22 +55,38 @@ def nvcc_path() -> str:
     return p
 
 
-def build_product(force: bool = False, verbose_ptxas: bool = False) -> str:
-    if not force and _newer(PRODUCT_SO, _all_deps()):
-        return PRODUCT_SO
-    srcs = [os.path.join(CSRC, f) for f in HOST_SOURCES + DEVICE_SOURCES]
-    cmd = [nvcc_path(), "-std=c++17", "-O3", "-lineinfo",
-           "-gencode", "arch=compute_100a,code=sm_100a",
-           "-fmad=false",                      # parity: the reference never fuses multiply-add
-           "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-Wall",
-           "-cudart", "static", "-shared",
-           "-Xlinker", "-Bsymbolic",
-           "-DIWB_BUILDING=1",
-           "-o", PRODUCT_SO] + srcs
+def build_product(force: bool = False, verbose_ptxas: bool = False, out: str | None = None) -> str:
+    """Each translation unit is compiled to an object in parallel (the kernel templates dominate the build
+    time), then linked into one shared library.  IWB_QUICK=1 in the environment builds only the kernel variants
+    of the headline configuration (tuning builds; never committed or shipped that way)."""
+    target = out or PRODUCT_SO
+    if not force and _newer(target, _all_deps()):
+        return target
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = OBJ_DIR if not out else OBJ_DIR + "_" + os.path.splitext(os.path.basename(out))[0]
+    os.makedirs(obj_dir, exist_ok=True)
+    flags = ["-std=c++17", "-O3", "-lineinfo",
+             "-gencode", "arch=compute_100a,code=sm_100a",
+             "-fmad=false",                      # parity: the reference never fuses multiply-add
+             "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-Wall",
+             "-DIWB_BUILDING=1"]
+    if os.environ.get("IWB_QUICK") == "1":
+        flags.append("-DIWB_QUICK=1")
+    for d in os.environ.get("IWB_DEFS", "").split():
+        flags.append("-D" + d)
     if verbose_ptxas:
-        cmd.insert(1, "-Xptxas=-v")
-    _run(cmd)
-    return PRODUCT_SO
+        flags.append("-Xptxas=-v")
+
+    def compile_one(name: str) -> str:
+        obj = os.path.join(obj_dir, os.path.splitext(name)[0] + ".o")
+        _run([nvcc_path()] + flags + ["-c", os.path.join(CSRC, name), "-o", obj])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(compile_one, DEVICE_SOURCES + HOST_SOURCES))
+    _run([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-shared",
+          "-Xlinker", "-Bsymbolic", "-o", target] + objs)
+    return target
 
 
 def build_emulator(force: bool = False) -> str:
@@ -79,8 +96,7 @@ def build_emulator(force: bool = False) -> str:
     srcs = [os.path.join(CSRC, f) for f in HOST_SOURCES]
     cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden",
            "-Wl,-Bsymbolic", "-DIWB_EMU=1", "-DIWB_BUILDING=1", "-Wall", "-o", EMU_SO] + srcs
-    for f in DEVICE_SOURCES:
-        cmd += ["-x", "c++", os.path.join(CSRC, f)]
+    cmd += ["-x", "c++", os.path.join(CSRC, "pipeline.cu")]   # kernel bodies as host loops (stream2.cu is device-only)
     _run(cmd)
     return EMU_SO
 

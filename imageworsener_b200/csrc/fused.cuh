@@ -90,6 +90,13 @@ struct FastPlan {
   int chunk_rows = 0;
   size_t v_smem = 0, h_smem = 0;
   int v_nr_max = 0, h_nb_max = 0;
+  // second-generation kernels (stream2.cuh); used when the call's buffers also meet the TMA alignment rules
+  int v2 = 0;
+  struct Sched2 *s2v = nullptr, *s2h = nullptr;   // (pointers: stream2.cuh is included after this header)
+  struct Quant2 *q2 = nullptr;                    // [4]
+  int same_tables = 0;
+  int strip2 = 0, seg2 = 0;                        // 0: sized per launch to one wave of CTAs
+  int ncols_pad = 0;
 };
 
 #if !defined(IWB_EMU)

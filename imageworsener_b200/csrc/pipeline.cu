@@ -10,13 +10,16 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "iwb_internal.h"
 #include "kernels.cuh"
 #if !defined(IWB_EMU)
+#include <cuda_runtime.h>
 #include "fused.cuh"
+#include "stream2.cuh"
 #endif
 
 // ------------------------------------------------------------------------------------------------------
@@ -224,6 +227,8 @@ struct iwb200_job {
   void *d_out = nullptr; size_t d_out_bytes = 0;
 #if !defined(IWB_EMU)
   FastPlan fused;
+  struct s2_tables { Sched2 v, h; Quant2 q[4]; };
+  std::unique_ptr<s2_tables> s2_store;
 #endif
 
   // All plan tables (weight lists, colour tables, schedules) are packed into a few arena chunks and copied
@@ -522,6 +527,62 @@ bool dispatch_h(int S, int NCH, int EPI, const HStreamParams &p, dim3 g, size_t 
 }
 #endif
 
+// Schedule in the layout of the second-generation kernels: [n_in + 16][SS] weights (SS = S rounded up to even, so
+// every row starts on 16 bytes for the bulk copies; the padding rows cover the last stage's overhang).
+bool upload_sched2(iwb200_job *job, const HostSched &hs, int n_in, int n_out, Sched2 *d) {
+  const int S = hs.S, SS = (S + 1) & ~1;
+  std::vector<double> w((size_t)(n_in + 16) * SS, 0.0);
+  for (int r = 0; r < n_in; r++)
+    for (int k = 0; k < S; k++) w[(size_t)r * SS + k] = hs.w[(size_t)r * S + k];
+  d->w = job->upload(w.data(), w.size());
+  d->first = job->upload(hs.first.data(), hs.first.size());
+  d->last = job->upload(hs.last.data(), hs.last.size());
+  d->n_in = n_in; d->n_out = n_out;
+  return d->w && d->first && d->last;
+}
+
+// FP32 decision tables of one channel (threshold-table mode) for quantise8_v2; false = shape not supported.
+bool build_quant2(iwb200_job *job, const std::vector<double> &thr, Quant2 *q) {
+  const int n = (int)thr.size();
+  if (n < 2 || n > 256) return false;
+  const int top = n - 1;
+  std::vector<float> lof(n + 2), inv(n + 2);
+  double worst = 1.0;
+  for (int k = 0; k < n; k++) {
+    const double lo = thr[k], hi = k < top ? thr[k + 1] : 2.0;
+    lof[k] = (float)lo;
+    if (k < top && hi > lo) worst = std::max(worst, hi / (hi - lo));
+  }
+  if (lof[0] != 0.0f || lof[top] != 1.0f) return false;         // levels must span exactly [0, 1]
+  lof[n] = 3.0f; lof[n + 1] = 3.0f;
+  for (int k = 0; k < n; k++) {
+    const float hif = k < top ? lof[k + 1] : 2.0f;
+    if (!(hif > lof[k])) return false;
+    inv[k] = (float)(1.0 / ((double)hif - (double)lof[k]));
+  }
+  inv[n] = inv[n + 1] = 0.0f;
+  std::vector<unsigned char> blob(IWB2_TAB_BYTES, 0);
+  float4 *e4 = (float4 *)blob.data();
+  for (int k = 0; k < 258; k++) e4[k] = k <= n ? make_float4(lof[k], inv[k], lof[k + 1], inv[k + 1]) : make_float4(3.0f, 0.0f, 3.0f, 0.0f);
+  double *thr_d = (double *)(blob.data() + IWB2_TAB_THR);
+  for (int k = 0; k < 258; k++) thr_d[k] = k < n ? thr[k] : 2.0;
+  // bucket i = [i/NHINT, (i+1)/NHINT): its samples must lie in level hint[i] or hint[i] + 1
+  uint16_t *hint = (uint16_t *)(blob.data() + IWB2_TAB_HINT);
+  int lev = 0;
+  for (int i = 0; i <= IWB2_NHINT; i++) {
+    const float a = (float)i / (float)IWB2_NHINT, b = (float)(i + 1) / (float)IWB2_NHINT;
+    while (lev + 1 <= top && lof[lev + 1] <= a) lev++;
+    if (lev + 2 <= top && lof[lev + 2] < b) return false;       // three levels in one bucket
+    hint[i] = (uint16_t)lev;
+  }
+  for (int i = IWB2_NHINT + 1; i < IWB2_NHINT + 8; i++) hint[i] = hint[IWB2_NHINT];
+  q->top = top;
+  q->margin = (float)(2e-6 + 8.0 * 2.4e-7 * worst);
+  if (q->margin > 0.004f) return false;
+  q->blob = job->upload(blob.data(), blob.size());
+  return q->blob != nullptr;
+}
+
 // nr/nb: input samples of the longest strip/segment; nout: outputs tracked (strip/segment + still-open predecessors)
 size_t v_smem_bytes(int nr, int S, int nout, int nc) {
   const int nw = nc >= 4 ? nc / 4 : 1, tb = IWB_V_TB;
@@ -688,15 +749,99 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
   f->vfirst = hv.first;
   f->vlast = hv.last;
   f->enabled = 1;
+
+  // second generation: threshold-table epilogues with one dither family, at most 8 open windows per axis
+  f->v2 = 0;
+  f->ncols_pad = (ncols + 3) & ~3;
+  {
+    const char *o = iwb_option(ctx, "cuda:gen");
+    const bool want = !(o && atoi(o) == 1);
+    const bool s_ok = hv.S <= 8 && hh.S <= 8 && hv.S != 7 && hh.S != 7;
+    if (want && s_ok && (f->epi == 1 || f->epi == 3 || f->epi == 4) && iwb2_tensor_maps_available()) {
+      static_assert(sizeof(Sched2) > 0 && sizeof(Quant2) > 0, "stream2.cuh");
+      job->s2_store.reset(new iwb200_job::s2_tables());
+      f->s2v = &job->s2_store->v; f->s2h = &job->s2_store->h; f->q2 = job->s2_store->q;
+      bool ok = upload_sched2(job, hv, job->in_h, job->out.height, f->s2v) && upload_sched2(job, hh, job->in_w, job->out.width, f->s2h);
+      f->same_tables = 1;
+      for (int p = 0; p < nch && ok; p++) {
+        ok = build_quant2(job, job->thr_host[p], &f->q2[p]);
+        if (p && job->thr_host[p] != job->thr_host[0]) f->same_tables = 0;
+      }
+      if (const char *o2 = iwb_option(ctx, "cuda:strip2")) f->strip2 = std::max(8, atoi(o2) & ~7);
+      if (const char *o2 = iwb_option(ctx, "cuda:seg2")) f->seg2 = std::max(4, atoi(o2) & ~3);
+      f->v2 = ok ? 1 : 0;
+    }
+  }
 }
 
 static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const DevOutput &out, int r0, int r1,
                       iwb_stream stream) {
   if (!f->interT) {
-    f->interT = (float *)job->scratch((size_t)job->in_w * f->nch * f->pitch_j * sizeof(float));
+    const size_t bytes = (size_t)std::max(job->in_w * f->nch, f->ncols_pad) * f->pitch_j * sizeof(float);
+    f->interT = (float *)job->scratch(bytes);
     if (!f->interT) return false;
+    cudaMemsetAsync(f->interT, 0, bytes, stream);   // rows past the end of a partial row group are read (and ignored)
   }
   const int nch = f->nch;
+  // second-generation kernels: TMA needs 16-byte aligned rows
+  const uint8_t *src0 = in.pix + (ptrdiff_t)(in.y0 - in.row_origin) * (ptrdiff_t)in.bpr + (size_t)in.x0 * nch;
+  if (f->v2 && in.bpr % 16 == 0 && ((uintptr_t)src0 & 15) == 0) {
+    for (int c0 = r0; c0 < r1; c0 += f->chunk_rows) {
+      const int c1 = std::min(r1, c0 + f->chunk_rows);
+      V2Params vp;
+      vp.src = src0; vp.bpr = in.bpr; vp.ncols = job->in_w * nch; vp.lut = f->lut; vp.sc = *f->s2v;
+      vp.tm_row0 = f->vfirst[c0]; vp.tm_rows = f->vlast[c1 - 1] - f->vfirst[c0] + 1;
+      vp.inter = f->interT; vp.ncols_pad = f->ncols_pad; vp.row_lo = c0; vp.row_hi = c1;
+      // strips / segments sized so that one launch is (at most) one full wave of resident CTAs: every SM gets the
+      // same share and the halo a strip / segment re-reads is as small as the parallelism allows
+      const int sms = iwb2_sm_count();
+      const int colblocks = (vp.ncols + 128 * IWB2_V_WARPS - 1) / (128 * IWB2_V_WARPS);
+      int strip = f->strip2;
+      if (strip <= 0) {
+        const int slots = sms * iwb2_v_ctas_per_sm(f->SV, v2_smem_bytes(f->SV, 512));
+        const int nstrips = std::max(1, slots / colblocks);
+        strip = std::min(480, std::max(32, (((c1 - c0) + nstrips - 1) / nstrips + 7) & ~7));
+      }
+      vp.strip = strip;
+      dim3 gv((unsigned)colblocks, (unsigned)((c1 - c0 + strip - 1) / strip));
+      {
+        prof_scope ps(job, 5, stream);
+        if (!iwb2_launch_v(f->SV, vp, gv, v2_smem_bytes(f->SV, strip + f->SV), (cudaStream_t)stream))
+          return fail(job, "fast path: no vertical kernel variant (gen 2)");
+        g_launches++;
+      }
+      H2Params hp;
+      hp.inter = f->interT; hp.ncols_pad = f->ncols_pad; hp.row_lo = c0; hp.row_hi = c1; hp.sc = *f->s2h;
+      hp.out_w = out.width; hp.out = out; hp.ch_g = f->ch_g; hp.same_tables = f->same_tables; hp.jump = job->d_jump;
+      for (int p = 0; p < 4; p++) { hp.ch[p] = job->cout[p < nch ? p : 0]; hp.q[p] = f->q2[p < nch ? p : 0]; }
+      const int groups = (c1 - c0 + 31) / 32;
+      const int rowblocks = (groups + IWB2_H_WARPS - 1) / IWB2_H_WARPS;
+      const int ntab = f->same_tables ? 1 : nch;
+      int seg = f->seg2;
+      if (seg <= 0) {
+        const int slots = sms * iwb2_h_ctas_per_sm(f->SH, nch, f->epi, h2_smem_bytes(f->SH, nch, ntab, 512));
+        const int nsegs = std::max(1, slots / rowblocks);
+        seg = std::min(480, std::max(64, ((out.width + nsegs - 1) / nsegs + 3) & ~3));
+      }
+      hp.seg = seg;
+      dim3 gh((unsigned)((out.width + seg - 1) / seg), (unsigned)rowblocks);
+      {
+        prof_scope ps(job, 1, stream);
+        if (!iwb2_launch_h(f->SH, nch, f->epi, hp, gh, h2_smem_bytes(f->SH, nch, ntab, seg + f->SH), (cudaStream_t)stream))
+          return fail(job, "fast path: no horizontal kernel variant (gen 2)");
+        g_launches++;
+      }
+      if (job->negate) {
+        PostParams pp;
+        pp.out = out; pp.row0 = c0; pp.row1 = c1; pp.negate = 1; pp.alpha_ch = -1; pp.clear_transparent = 0;
+        for (int c = 0; c < 4; c++) pp.maxcode[c] = c < job->ctx->out_nch ? job->ctx->out_ci[c].maxcode : 0;
+        prof_scope ps(job, 4, stream);
+        launch<PostBody>(pp, (size_t)(c1 - c0) * out.width, stream);
+      }
+    }
+    if (cudaGetLastError() != cudaSuccess) return fail(job, "fast path: kernel launch failed (gen 2)");
+    return true;
+  }
   for (int c0 = r0; c0 < r1; c0 += f->chunk_rows) {
     const int c1 = std::min(r1, c0 + f->chunk_rows);
     VStreamParams vp;
