@@ -79,7 +79,7 @@ struct FastPlan {
   int nch = 0;
   int SV = 0, SH = 0, NC = 0;
   AxisSched sv{}, sh{};
-  std::vector<int> vfirst, vlast;   // host copies for band planning
+  std::vector<int> vfirst, vlast, hlast;   // host copies for band planning / uniform-range detection
   const double *lut = nullptr;
   FastQuant fq[4]{};
   float *interT = nullptr;
@@ -96,7 +96,9 @@ struct FastPlan {
   struct Quant2 *q2 = nullptr;                    // [4]
   int same_tables = 0;
   int strip2 = 0, seg2 = 0;                        // 0: sized per launch to one wave of CTAs
+  int uniform = 1;
   int ncols_pad = 0;
+  size_t inter_pad = 0;                            // floats of padding in front of the intermediate
 };
 
 #if !defined(IWB_EMU)

@@ -527,14 +527,16 @@ bool dispatch_h(int S, int NCH, int EPI, const HStreamParams &p, dim3 g, size_t 
 }
 #endif
 
-// Schedule in the layout of the second-generation kernels: [n_in + 16][SS] weights (SS = S rounded up to even, so
-// every row starts on 16 bytes for the bulk copies; the padding rows cover the last stage's overhang).
+// Schedule in the layout of the second-generation kernels: rows [-IWB2_WPAD, n_in + IWB2_WPAD) of SS weights (SS = S
+// rounded up to even, so every row starts on 16 bytes for the bulk copies); the padding rows are zero weights for
+// stages that start before the first input or end after the last one.
 bool upload_sched2(iwb200_job *job, const HostSched &hs, int n_in, int n_out, Sched2 *d) {
   const int S = hs.S, SS = (S + 1) & ~1;
-  std::vector<double> w((size_t)(n_in + 16) * SS, 0.0);
+  std::vector<double> w((size_t)(n_in + 2 * IWB2_WPAD) * SS, 0.0);
   for (int r = 0; r < n_in; r++)
-    for (int k = 0; k < S; k++) w[(size_t)r * SS + k] = hs.w[(size_t)r * S + k];
-  d->w = job->upload(w.data(), w.size());
+    for (int k = 0; k < S; k++) w[(size_t)(r + IWB2_WPAD) * SS + k] = hs.w[(size_t)r * S + k];
+  const double *base = job->upload(w.data(), w.size());
+  d->w = base ? base + (size_t)IWB2_WPAD * SS : nullptr;
   d->first = job->upload(hs.first.data(), hs.first.size());
   d->last = job->upload(hs.last.data(), hs.last.size());
   d->n_in = n_in; d->n_out = n_out;
@@ -748,6 +750,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
   }
   f->vfirst = hv.first;
   f->vlast = hv.last;
+  f->hlast = hh.last;
   f->enabled = 1;
 
   // second generation: threshold-table epilogues with one dither family, at most 8 open windows per axis
@@ -756,8 +759,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
   {
     const char *o = iwb_option(ctx, "cuda:gen");
     const bool want = !(o && atoi(o) == 1);
-    const bool s_ok = hv.S <= 8 && hh.S <= 8 && hv.S != 7 && hh.S != 7;
-    if (want && s_ok && (f->epi == 1 || f->epi == 3 || f->epi == 4) && iwb2_tensor_maps_available()) {
+    if (want && iwb2_supported(hv.S, hh.S, nch, f->epi) && iwb2_tensor_maps_available()) {
       static_assert(sizeof(Sched2) > 0 && sizeof(Quant2) > 0, "stream2.cuh");
       job->s2_store.reset(new iwb200_job::s2_tables());
       f->s2v = &job->s2_store->v; f->s2h = &job->s2_store->h; f->q2 = job->s2_store->q;
@@ -769,6 +771,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
       }
       if (const char *o2 = iwb_option(ctx, "cuda:strip2")) f->strip2 = std::max(8, atoi(o2) & ~7);
       if (const char *o2 = iwb_option(ctx, "cuda:seg2")) f->seg2 = std::max(4, atoi(o2) & ~3);
+      if (const char *o2 = iwb_option(ctx, "cuda:uniform")) f->uniform = atoi(o2) != 0;
       f->v2 = ok ? 1 : 0;
     }
   }
@@ -777,7 +780,9 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
 static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const DevOutput &out, int r0, int r1,
                       iwb_stream stream) {
   if (!f->interT) {
-    const size_t bytes = (size_t)std::max(job->in_w * f->nch, f->ncols_pad) * f->pitch_j * sizeof(float);
+    // gen 2 reads whole stages: up to IWB2_WPAD pixel columns before the first / after the last column of a row group
+    f->inter_pad = (size_t)IWB2_WPAD * 4 * 32;
+    const size_t bytes = ((size_t)std::max(job->in_w * f->nch, f->ncols_pad) * f->pitch_j + 2 * f->inter_pad) * sizeof(float);
     f->interT = (float *)job->scratch(bytes);
     if (!f->interT) return false;
     cudaMemsetAsync(f->interT, 0, bytes, stream);   // rows past the end of a partial row group are read (and ignored)
@@ -788,47 +793,26 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
   if (f->v2 && in.bpr % 16 == 0 && ((uintptr_t)src0 & 15) == 0) {
     for (int c0 = r0; c0 < r1; c0 += f->chunk_rows) {
       const int c1 = std::min(r1, c0 + f->chunk_rows);
-      V2Params vp;
+      V2Job vj{};
+      V2Params &vp = vj.p;
       vp.src = src0; vp.bpr = in.bpr; vp.ncols = job->in_w * nch; vp.lut = f->lut; vp.sc = *f->s2v;
       vp.tm_row0 = f->vfirst[c0]; vp.tm_rows = f->vlast[c1 - 1] - f->vfirst[c0] + 1;
-      vp.inter = f->interT; vp.ncols_pad = f->ncols_pad; vp.row_lo = c0; vp.row_hi = c1;
-      // strips / segments sized so that one launch is (at most) one full wave of resident CTAs: every SM gets the
-      // same share and the halo a strip / segment re-reads is as small as the parallelism allows
-      const int sms = iwb2_sm_count();
-      const int colblocks = (vp.ncols + 128 * IWB2_V_WARPS - 1) / (128 * IWB2_V_WARPS);
-      int strip = f->strip2;
-      if (strip <= 0) {
-        const int slots = sms * iwb2_v_ctas_per_sm(f->SV, v2_smem_bytes(f->SV, 512));
-        const int nstrips = std::max(1, slots / colblocks);
-        strip = std::min(480, std::max(32, (((c1 - c0) + nstrips - 1) / nstrips + 7) & ~7));
-      }
-      vp.strip = strip;
-      dim3 gv((unsigned)colblocks, (unsigned)((c1 - c0 + strip - 1) / strip));
+      vp.inter = f->interT + f->inter_pad; vp.ncols_pad = f->ncols_pad; vp.row_base = c0; vp.row_lo = c0; vp.row_hi = c1;
+      vj.S = f->SV; vj.last_host = f->vlast.data(); vj.strip_override = f->strip2; vj.allow_uniform = f->uniform;
       {
         prof_scope ps(job, 5, stream);
-        if (!iwb2_launch_v(f->SV, vp, gv, v2_smem_bytes(f->SV, strip + f->SV), (cudaStream_t)stream))
-          return fail(job, "fast path: no vertical kernel variant (gen 2)");
+        if (!iwb2_run_v(vj, (cudaStream_t)stream)) return fail(job, "fast path: no vertical kernel variant (gen 2)");
         g_launches++;
       }
-      H2Params hp;
-      hp.inter = f->interT; hp.ncols_pad = f->ncols_pad; hp.row_lo = c0; hp.row_hi = c1; hp.sc = *f->s2h;
-      hp.out_w = out.width; hp.out = out; hp.ch_g = f->ch_g; hp.same_tables = f->same_tables; hp.jump = job->d_jump;
+      H2Job hj{};
+      H2Params &hp = hj.p;
+      hp.inter = f->interT + f->inter_pad; hp.ncols_pad = f->ncols_pad; hp.row_lo = c0; hp.row_hi = c1; hp.sc = *f->s2h;
+      hp.out_w = out.width; hp.out = out; hp.same_tables = f->same_tables; hp.jump = job->d_jump;
       for (int p = 0; p < 4; p++) { hp.ch[p] = job->cout[p < nch ? p : 0]; hp.q[p] = f->q2[p < nch ? p : 0]; }
-      const int groups = (c1 - c0 + 31) / 32;
-      const int rowblocks = (groups + IWB2_H_WARPS - 1) / IWB2_H_WARPS;
-      const int ntab = f->same_tables ? 1 : nch;
-      int seg = f->seg2;
-      if (seg <= 0) {
-        const int slots = sms * iwb2_h_ctas_per_sm(f->SH, nch, f->epi, h2_smem_bytes(f->SH, nch, ntab, 512));
-        const int nsegs = std::max(1, slots / rowblocks);
-        seg = std::min(480, std::max(64, ((out.width + nsegs - 1) / nsegs + 3) & ~3));
-      }
-      hp.seg = seg;
-      dim3 gh((unsigned)((out.width + seg - 1) / seg), (unsigned)rowblocks);
+      hj.S = f->SH; hj.nch = nch; hj.epi = f->epi; hj.last_host = f->hlast.data(); hj.seg_override = f->seg2; hj.allow_uniform = f->uniform;
       {
         prof_scope ps(job, 1, stream);
-        if (!iwb2_launch_h(f->SH, nch, f->epi, hp, gh, h2_smem_bytes(f->SH, nch, ntab, seg + f->SH), (cudaStream_t)stream))
-          return fail(job, "fast path: no horizontal kernel variant (gen 2)");
+        if (!iwb2_run_h(hj, (cudaStream_t)stream)) return fail(job, "fast path: no horizontal kernel variant (gen 2)");
         g_launches++;
       }
       if (job->negate) {

@@ -4,19 +4,21 @@
 // reference: src/imagew-resize.c:346-361, src/imagew-main.c:831-927, :929-1155) but every warp is an independent
 // pipeline fed by the TMA engine:
 //
-//   * each warp owns a ring of NST stages in shared memory; one elected lane posts the byte count on the
-//     stage's mbarrier and a few lanes issue cp.async.bulk (TMA, SASS UBLKCP) copies: G input rows of 128 bytes
-//     + the G schedule rows of weights (vertical), or KP pixel columns x 32 rows of the FP32 intermediate as ONE
-//     contiguous block + KP schedule rows (horizontal).  No thread ever issues a per-sample load, there is no
-//     __syncthreads in the steady state, and shared memory does not grow with the strip / segment length;
+//   * each warp owns a ring of stages in shared memory; one elected lane posts the byte count on the stage's
+//     mbarrier and issues the copies (SASS UTMALDG / UBLKCP): a 2-D tensor tile of G input rows x 128 bytes + the G
+//     schedule rows of weights (vertical), or KP pixel columns x 32 rows of the FP32 intermediate as ONE
+//     contiguous block + KP schedule rows (horizontal).  No thread ever issues a per-sample global load, there is
+//     no __syncthreads in the steady state, and shared memory does not grow with the strip / segment length;
 //   * the FP32 intermediate is stored "blocked transposed": inter[row group of 32][column][32 rows], so the
 //     horizontal kernel (lanes = 32 rows, schedule warp-uniform) gets a column range of its row group with one
 //     contiguous bulk copy and reads it with conflict-free LDS.32 at immediate offsets, while the vertical
 //     kernel still writes whole 32-byte sectors (8 finished rows of a column);
+//   * where the schedule is regular (integer reduction factors away from the border) a whole cycle of S outputs
+//     is straight-line code (stream2_dev.cuh); elsewhere per-output trip counts come from the schedule tables;
 //   * the 8-bit epilogue is branch-free in the common case: clamp by saturation, bucket -> level by one u16 and
 //     one float4 read, fraction by multiplication with the stored reciprocal width, decision against the
-//     ordered / random / 0.5 threshold unless it falls inside the FP32 error margin (then the exact FP64
-//     quantiser of kernels.cuh decides, so codes stay bit-identical).
+//     ordered / random / 0.5 threshold unless it falls inside the FP32 error margin (then an exact FP64
+//     decision on the same tables is taken, so codes stay bit-identical).
 #pragma once
 
 #if !defined(IWB_EMU)
@@ -28,7 +30,7 @@
 #define IWB2_V_MINB 2            // resident CTAs per SM the register allocation aims at
 #endif
 #ifndef IWB2_V_G
-#define IWB2_V_G 8               // input rows per stage
+#define IWB2_V_G 8               // general path: input rows per stage
 #endif
 #ifndef IWB2_V_NST
 #define IWB2_V_NST 4
@@ -37,18 +39,35 @@
 #define IWB2_H_WARPS 4
 #endif
 #ifndef IWB2_H_KP
-#define IWB2_H_KP 4              // pixel columns per stage
+#define IWB2_H_KP 4              // general path: pixel columns per stage
 #endif
 #ifndef IWB2_H_NST
 #define IWB2_H_NST 4
 #endif
+#ifndef IWB2_U_NST
+#define IWB2_U_NST 2             // uniform path: stages (one cycle of S outputs each)
+#endif
+#ifndef IWB2_DEFER
+#define IWB2_DEFER 1             // deferred adds (stream2_dev.cuh); 0 trades them for registers / occupancy
+#endif
 #define IWB2_OST_PITCH 132       // bytes per output staging row (33 words: lane-private banks)
 #define IWB2_NHINT 4096
+#define IWB2_WPAD 64             // schedule rows of zero weights before row 0 and after the last row
+#define IWB2_MAX_GU 16           // longest uniform cycle (inputs) the kernels are built for
 
 struct Sched2 {                  // device pointers
-  const double *w;               // [n_in + pad][SS], SS = S rounded up to even; idle slots and padding rows = +0.0
+  const double *w;               // row r at w + r*SS, r in [-IWB2_WPAD, n_in + IWB2_WPAD); SS = S rounded up to even
   const int *first, *last;       // [n_out] window of each output
   int n_in, n_out;
+};
+
+// How one launch splits its outputs over CTAs (rows for the vertical kernel, pixels for the horizontal one):
+// n_u uniform parts of u_len outputs covering [u_lo, u_hi), then general parts of g_len outputs covering what is
+// left before u_lo and after u_hi.  In the uniform range output o completes at input u_ref_last + step*(o - u_ref_o).
+struct Part2 {
+  int n_u, u_lo, u_hi, u_len;
+  int g_len;
+  int u_ref_o, u_ref_last;
 };
 
 // Decision tables of one output channel, one 16-byte aligned blob (copied to shared memory by one bulk copy):
@@ -71,47 +90,47 @@ struct V2Params {
   int ncols;                     // byte columns (= in_w * channels)
   const double *lut;             // [256] code -> linear
   Sched2 sc;
-  float *inter;                  // blocked transposed intermediate, rows relative to row_lo
+  float *inter;                  // blocked transposed intermediate
   int ncols_pad;                 // columns per row group in `inter`
+  int row_base;                  // output row stored as row 0 of `inter`
   int row_lo, row_hi;            // output rows of this launch
-  int strip;                     // output rows per CTA row (multiple of 32)
+  Part2 part;                    // strips (lengths are multiples of 8 rows counted from row_base)
 };
 
 struct H2Params {
   const float *inter;
   int ncols_pad;
-  int row_lo, row_hi;
+  int row_lo, row_hi;            // output rows of this launch; row_lo is row 0 of `inter`
   Sched2 sc;                     // in pixels
-  int seg;                       // output pixels per CTA (multiple of 4)
+  Part2 part;                    // segments of output pixels (lengths are multiples of 4)
   int out_w;
   DevOutput out;
   DevChanOut ch[4];
-  const DevChanOut *ch_g;        // same, in global memory (exact path)
   Quant2 q[4];
   int same_tables;               // every channel uses q[0]'s tables
   const iwb_affine_t *jump;
 };
 
-static inline size_t v2_smem_bytes(int S, int nout) {
-  const int SS = (S + 1) & ~1;
-  const size_t stage = (size_t)IWB2_V_G * 128 + (size_t)IWB2_V_G * SS * 8;
-  const size_t warp_bytes = (IWB2_V_NST * stage + 8 * 4 * 32 * 4 + IWB2_V_NST * 8 + 127) & ~(size_t)127;
-  return 256 * 16 * 8 + IWB2_V_WARPS * warp_bytes + (size_t)nout * 4 + 16;
-}
+// Host-side description of one pass over a chunk of output rows; the module sizes strips / segments (one wave of
+// resident CTAs, uniform parts where the schedule allows) and launches.
+struct V2Job {
+  V2Params p;                    // everything but `part`
+  int S;
+  const int *last_host;          // [n_out] host copy of the schedule's window ends
+  int strip_override;            // > 0: rows per uniform strip (tuning)
+  int allow_uniform;
+};
+struct H2Job {
+  H2Params p;                    // everything but `part`
+  int S, nch, epi;
+  const int *last_host;
+  int seg_override;
+  int allow_uniform;
+};
 
-static inline size_t h2_smem_bytes(int S, int nch, int ntab, int nout) {
-  const int SS = (S + 1) & ~1;
-  const size_t stage = (size_t)IWB2_H_KP * nch * 128 + (size_t)IWB2_H_KP * SS * 8;
-  const size_t warp_bytes = (IWB2_H_NST * stage + 32 * IWB2_OST_PITCH + IWB2_H_NST * 8 + 127) & ~(size_t)127;
-  return IWB2_H_WARPS * warp_bytes + (size_t)ntab * IWB2_TAB_BYTES + 64 * 4 + 16 + (size_t)nout * 4 + 16;
-}
-
-// launchers (stream2.cu); false = no kernel variant for this shape
 bool iwb2_tensor_maps_available();
-int iwb2_sm_count();
-int iwb2_v_ctas_per_sm(int S, size_t smem);
-int iwb2_h_ctas_per_sm(int S, int nch, int epi, size_t smem);
-bool iwb2_launch_v(int S, const V2Params &p, dim3 grid, size_t smem, cudaStream_t st);
-bool iwb2_launch_h(int S, int nch, int epi, const H2Params &p, dim3 grid, size_t smem, cudaStream_t st);
+bool iwb2_run_v(const V2Job &job, cudaStream_t st);   // false: no kernel variant / launch problem
+bool iwb2_run_h(const H2Job &job, cudaStream_t st);
+bool iwb2_supported(int SV, int SH, int nch, int epi);
 
 #endif  // !IWB_EMU

@@ -1,0 +1,665 @@
+// stream2_dev.cuh -- device code of the second-generation streaming kernels (design: stream2.cuh).
+//
+// Each kernel has two code paths chosen per CTA:
+//   * "uniform": the strip / segment lies where the schedule is regular -- output o completes exactly STEP inputs
+//     after output o-1 (any integer reduction factor, away from the image border).  One cycle of S outputs then
+//     consumes exactly S*STEP inputs = one pipeline stage, and the whole cycle is straight-line code: every
+//     shared-memory access has an immediate offset, slots are compile-time registers, there is no loop or ring
+//     bookkeeping per input, and the only branches are the (warp-uniform) emission guards;
+//   * "general": any monotone contiguous-window schedule (per-output trip counts from the schedule tables).
+// Both paths use deferred adds (the product of input i is added while input i+1 is multiplied), so no FP64
+// instruction of an input depends on another one of the same input; and in-place rotation of the operands (the
+// value of input i+1 replaces the value of input i right after its last use).  The order of the additions into
+// each accumulator is the reference's (ascending source index, one DMUL + one DADD per tap, no FMA).
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "iwb_internal.h"
+#include "kernels.cuh"
+#include "stream2.cuh"
+
+// ---- mbarrier + bulk copy primitives -----------------------------------------------------------------
+__device__ __forceinline__ unsigned s2_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void s2_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void s2_mbar_expect(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void s2_mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra W_%=;\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void s2_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void s2_tma_2d(unsigned dst, const CUtensorMap *tm, int c0, int c1, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ bool s2_elect() {                    // one lane of the (converged) warp
+  unsigned pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void s2_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ unsigned s2_lds32(unsigned a) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float s2_ldsf(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double2 s2_ldsw(unsigned a) {        // one pair of weights
+  double x, y;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+  return make_double2(x, y);
+}
+__device__ __forceinline__ int s2_floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+// Which strip / segment does CTA index `id` process?  Uniform ones first, then the general head and tail.
+__device__ __forceinline__ void s2_decode_part(const Part2 &pt, int id, int lo, int hi, int *a, int *b, bool *uni) {
+  if (id < pt.n_u) {
+    *uni = true;
+    *a = pt.u_lo + id * pt.u_len;
+    *b = min(*a + pt.u_len, pt.u_hi);
+    return;
+  }
+  *uni = false;
+  int g = id - pt.n_u;
+  const int nh = (pt.u_lo - lo + pt.g_len - 1) / pt.g_len;
+  if (g < nh) {
+    *a = lo + g * pt.g_len;
+    *b = min(*a + pt.g_len, pt.u_lo);
+  } else {
+    g -= nh;
+    *a = pt.u_hi + g * pt.g_len;
+    *b = min(*a + pt.g_len, hi);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// vertical kernel.  Warp = 128 adjacent byte columns (lane = 4 of them, one 32-bit word per row), strip of
+// output rows; walks the input rows of the strip once.  Loads run ahead of the arithmetic: while row i is
+// multiplied, the table values of row i+1 and the ring word of row i+2 are already in flight.
+// ---------------------------------------------------------------------------------------------------------
+template <int S, int STEP>
+__global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
+    iwb_v2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_u, const V2Params p) {
+  constexpr int SS = (S + 1) & ~1;
+  constexpr int G = IWB2_V_G, NST = IWB2_V_NST;                 // general path: rows per stage, stages
+  constexpr int STAGE = G * 128 + G * SS * 8;                   // bytes: input rows, then weights
+  constexpr int GU = STEP > 0 ? S * STEP : 4, NSTU = IWB2_U_NST;   // uniform path: one cycle per stage
+  constexpr int STAGE_U = (GU * 128 + GU * SS * 8 + 127) & ~127;
+  constexpr int RING = NST * STAGE > NSTU * STAGE_U ? NST * STAGE : NSTU * STAGE_U;
+  constexpr int WARP_BYTES = (RING + 8 * 4 * 32 * 4 + 8 * 8 + 127) & ~127;   // TMA tiles land on 128-byte boundaries
+  static_assert(G >= 4 && NST >= 3 && GU >= 4 && NSTU >= 2, "pipeline depth");
+  static_assert((STAGE % 128) == 0 && (STAGE_U % 128) == 0, "stage alignment");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int o0, o1;
+  bool uni;
+  s2_decode_part(p.part, blockIdx.y, p.row_lo, p.row_hi, &o0, &o1, &uni);
+  if (STEP == 0) uni = false;
+
+  double *lut_s = (double *)smem_raw;                           // [256][16]
+  unsigned char *wbase = smem_raw + 256 * 16 * 8 + (size_t)warp * WARP_BYTES;
+  float *tbuf = (float *)(wbase + RING);                        // [8 rows][4 cols][32 lanes]
+  const unsigned bar0 = s2_addr(wbase + RING + 8 * 4 * 32 * 4);
+  int *last_s = (int *)(smem_raw + 256 * 16 * 8 + (size_t)IWB2_V_WARPS * WARP_BYTES);   // general path: [nout]
+  const int wcol0 = (blockIdx.x * IWB2_V_WARPS + warp) * 128;
+  const bool active = wcol0 < p.ncols;
+  const unsigned ring0 = s2_addr(wbase);
+  const int col0 = wcol0 + lane * 4;
+  const bool full = col0 + 4 <= p.ncols;
+
+  // general-path geometry (from the schedule tables)
+  int r0 = 0, nr = 0, ob = o0, nout = 0, nstg = 0;
+  // uniform-path geometry (closed form): cycle c = outputs [og0 + c*S, +S) = rows [R0 + c*GU, +GU)
+  int og0 = 0, ncyc = 0, R0 = 0;
+  if (uni) {
+    og0 = s2_floor_div(o0 - (S - 1), S) * S;
+    ncyc = (o1 - og0 + S - 1) / S;
+    R0 = p.part.u_ref_last + STEP * (og0 - p.part.u_ref_o) - STEP + 1;
+  } else {
+    r0 = p.sc.first[o0];
+    nr = p.sc.last[o1 - 1] - r0 + 1;
+    while (ob > 0 && p.sc.last[ob - 1] >= r0) ob--;             // first output still open at r0
+    nout = o1 - ob;
+    nstg = (nr + G - 1) / G;
+  }
+  // stage n of the general path = input rows [r0 + n*G, +G) x this warp's 128 byte columns as one TMA tile (rows /
+  // columns outside the tensor are zero-filled and never consumed) + the G schedule rows of weights
+  auto fill = [&](int n, int slot) {
+    if (s2_elect()) {
+      const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE;
+      s2_mbar_expect(bar, G * 128 + G * SS * 8);
+      s2_tma_2d(dst, &tmap, wcol0, r0 + n * G - p.tm_row0, bar);
+      s2_bulk_g2s(dst + G * 128, p.sc.w + (ptrdiff_t)(r0 + n * G) * SS, G * SS * 8, bar);
+    }
+  };
+  auto fill_u = [&](int n, int slot) {                          // uniform path: stage n = cycle n (+1 of overrun)
+    if (s2_elect()) {
+      const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE_U;
+      s2_mbar_expect(bar, GU * 128 + GU * SS * 8);
+      s2_tma_2d(dst, &tmap_u, wcol0, R0 + n * GU - p.tm_row0, bar);
+      s2_bulk_g2s(dst + GU * 128, p.sc.w + (ptrdiff_t)(R0 + n * GU) * SS, GU * SS * 8, bar);
+    }
+  };
+  if (active) {                                                 // start the pipeline before the table loads
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < 8; s++) s2_mbar_init(bar0 + 8 * s, 1);
+      s2_fence_async();
+    }
+    __syncwarp();
+    if (uni) {
+#pragma unroll
+      for (int s = 0; s < NSTU; s++)
+        if (s <= ncyc) fill_u(s, s);
+    } else {
+#pragma unroll
+      for (int s = 0; s < NST; s++)
+        if (s < nstg) fill(s, s);
+    }
+  }
+  for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) lut_s[i] = p.lut[i >> 4];
+  if (!uni)
+    for (int i = threadIdx.x; i < nout; i += blockDim.x) last_s[i] = p.sc.last[ob + i] - r0;
+  __syncthreads();
+  if (!active) return;
+
+  double acc[S][4], prod[S][4];                                 // slot accumulators and deferred products
+#pragma unroll
+  for (int s = 0; s < S; s++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) { acc[s][c] = 0.0; prod[s][c] = 0.0; }
+
+  const unsigned lut_lane = (lane & 15) * 8;                    // this lane's bank pair: bits 3..6 of the table offset
+  const char *lut_b = (const char *)lut_s;
+  auto lut_at = [&](unsigned off) { return *(const double *)(lut_b + off); };   // (the table base folds into the LDS immediate)
+  auto lookup1 = [&](unsigned x, int c) {                       // code * 128 bytes (16 copies of 8 bytes) + lane copy
+    const unsigned sh = c == 0 ? (x << 7) : (x >> (8 * c - 7));
+    return lut_at((sh & 0x7f80u) | lut_lane);
+  };
+  // one input row: drain last row's products into the accumulators, form this row's products (deferred), and
+  // replace each column's value by the next row's as soon as its products are formed
+  auto taps = [&](double (&vc)[4], unsigned xn, unsigned wrow) {
+    double2 w[SS / 2];
+#pragma unroll
+    for (int s2 = 0; s2 < SS / 2; s2++) w[s2] = s2_ldsw(wrow + 16 * s2);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+#pragma unroll
+      for (int s = 0; s < S; s++) {
+        if (IWB2_DEFER) {
+          acc[s][c] = __dadd_rn(acc[s][c], prod[s][c]);
+          prod[s][c] = __dmul_rn(vc[c], (s & 1) ? w[s >> 1].y : w[s >> 1].x);
+        } else {
+          acc[s][c] = __dadd_rn(acc[s][c], __dmul_rn(vc[c], (s & 1) ? w[s >> 1].y : w[s >> 1].x));
+        }
+      }
+      vc[c] = lookup1(xn, c);
+    }
+  };
+  // slot k is complete: add its pending products, hand the row to the transposing store, restart the slot
+  auto finish = [&](int k, int o) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) if (IWB2_DEFER) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
+    if (o >= o0 && o < o1) {
+      const int orel = o - p.row_base, tb = orel & 7;
+#pragma unroll
+      for (int c = 0; c < 4; c++) tbuf[(tb * 4 + c) * 32 + lane] = (float)acc[k][c];
+      if (tb == 7 || o == o1 - 1) {                             // 8 consecutive rows of each column: one 32-byte sector
+        const int base = orel - tb, cnt = tb + 1;
+        float *dst0 = p.inter + ((size_t)(base >> 5) * p.ncols_pad + col0) * 32 + (base & 31);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          if (full || col0 + c < p.ncols) {
+            float g[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) g[r] = tbuf[(r * 4 + c) * 32 + lane];
+            float *dst = dst0 + c * 32;
+            if (cnt == 8) {
+              *reinterpret_cast<float4 *>(dst) = make_float4(g[0], g[1], g[2], g[3]);
+              *reinterpret_cast<float4 *>(dst + 4) = make_float4(g[4], g[5], g[6], g[7]);
+            } else {
+#pragma unroll
+              for (int r = 0; r < 8; r++)
+                if (r < cnt) dst[r] = g[r];
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[k][c] = 0.0;
+  };
+
+  if (STEP > 0 && uni) {
+    // ---- uniform path --------------------------------------------------------------------------------
+    int slot = 0;
+    unsigned par = 0;
+    s2_mbar_wait(bar0, 0);
+    double vc[4];
+    {
+      const unsigned x0 = s2_lds32(ring0 + lane * 4);
+#pragma unroll
+      for (int c = 0; c < 4; c++) vc[c] = lookup1(x0, c);       // row 0
+    }
+    unsigned xn = s2_lds32(ring0 + lane * 4 + 128);             // row 1
+    for (int cyc = 0; cyc < ncyc; cyc++) {
+      const int nslot = slot + 1 == NSTU ? 0 : slot + 1;
+      const unsigned npar = nslot == 0 ? par ^ 1 : par;
+      const unsigned sb = ring0 + slot * STAGE_U + lane * 4, sbn = ring0 + nslot * STAGE_U + lane * 4;
+      const unsigned wb = ring0 + slot * STAGE_U + GU * 128;
+      const int og = og0 + cyc * S;
+#pragma unroll
+      for (int r = 0; r < GU; r++) {
+        if (r == GU - 2) s2_mbar_wait(bar0 + 8 * nslot, npar);  // the last two rows prefetch from the next stage
+        const unsigned xcur = xn;
+        xn = s2_lds32(r + 2 < GU ? sb + (r + 2) * 128 : sbn + (r + 2 - GU) * 128);   // row r+2
+        taps(vc, xcur, wb + r * SS * 8);                        // row r (values of row r+1 from xcur)
+        if ((r + 1) % STEP == 0) finish((r + 1) / STEP - 1, og + (r + 1) / STEP - 1);
+      }
+      __syncwarp();
+      if (cyc + NSTU <= ncyc) fill_u(cyc + NSTU, slot);
+      slot = nslot;
+      par = npar;
+    }
+    return;
+  }
+
+  // ---- general path ------------------------------------------------------------------------------------
+  // read position (ring words): stage / slot / parity; weights position: slot.  The read position runs two rows
+  // ahead of the weights of the row being consumed; a stage's slot is refilled when the read position leaves the
+  // FOLLOWING stage (the lag is shorter than a stage), so NST-2 stages are in flight.
+  int ld_stage = 0, ld_slot = 0, w_slot = 0;
+  unsigned parity = 0;
+  s2_mbar_wait(bar0, 0);
+  unsigned pin = ring0 + lane * 4;
+  unsigned pin_end = pin + G * 128;
+  unsigned pw = ring0 + G * 128;
+  unsigned pw_end = pw + G * SS * 8;
+  auto advance_load = [&]() {                                   // the read position leaves stage ld_stage
+    __syncwarp();
+    if (ld_stage >= 1 && ld_stage - 1 + NST < nstg) fill(ld_stage - 1 + NST, ld_slot == 0 ? NST - 1 : ld_slot - 1);
+    ld_stage++;
+    if (++ld_slot == NST) { ld_slot = 0; parity ^= 1; }
+    if (ld_stage < nstg) s2_mbar_wait(bar0 + 8 * ld_slot, parity);
+    pin = ring0 + ld_slot * STAGE + lane * 4;
+    pin_end = pin + G * 128;
+  };
+  auto next_word = [&]() {
+    const unsigned x = s2_lds32(pin);
+    pin += 128;
+    if (pin == pin_end) advance_load();
+    return x;
+  };
+  double vc[4];
+  {
+    const unsigned x0 = next_word();
+#pragma unroll
+    for (int c = 0; c < 4; c++) vc[c] = lookup1(x0, c);         // row 0
+  }
+  unsigned xn = next_word();                                    // row 1
+  int i = 0;                                                    // row being consumed (relative to r0)
+  auto row_step = [&]() {
+    taps(vc, xn, pw);
+    xn = next_word();                                           // row i+2
+    pw += SS * 8;
+    if (pw == pw_end) {
+      if (++w_slot == NST) w_slot = 0;
+      pw = ring0 + w_slot * STAGE + G * 128;
+      pw_end = pw + G * SS * 8;
+    }
+    i++;
+  };
+  for (int og = ob - (ob % S); og < o1; og += S) {
+#pragma unroll
+    for (int k = 0; k < S; k++) {
+      const int o = og + k;
+      if (o >= ob && o < o1) {                                  // warp-uniform
+        const int iend = last_s[o - ob];
+        while (i <= iend) row_step();
+        finish(k, o);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// horizontal kernel + 8-bit epilogue.  Warp = 32 rows (one row group) x one segment of output pixels.
+// EPI: 1 = no dither, 3 = ordered, 4 = random (all channels threshold-table mode, same dither).
+// ---------------------------------------------------------------------------------------------------------
+// ordered-dither matrices (reference: src/imagew-main.c:460-480), entry k means threshold (k + 0.5) / 64
+__constant__ unsigned char iwb2_ord[128] = {
+    0, 48, 12, 60, 3, 51, 15, 63, 32, 16, 44, 28, 35, 19, 47, 31, 8, 56, 4, 52, 11, 59, 7, 55, 40, 24, 36, 20, 43, 27, 39, 23,
+    2, 50, 14, 62, 1, 49, 13, 61, 34, 18, 46, 30, 33, 17, 45, 29, 10, 58, 6, 54, 9, 57, 5, 53, 42, 26, 38, 22, 41, 25, 37, 21,
+    3, 9, 17, 27, 25, 15, 7, 1, 11, 29, 37, 45, 43, 35, 23, 5, 19, 39, 51, 57, 55, 49, 33, 13, 31, 47, 59, 63, 61, 53, 41, 21,
+    30, 46, 58, 62, 60, 52, 40, 20, 18, 38, 50, 56, 54, 48, 32, 12, 10, 28, 36, 44, 42, 34, 22, 4, 2, 8, 16, 26, 24, 14, 6, 0};
+
+// The exact FP64 decision for a sample the FP32 test could not settle (reference: put_sample_convert_from_linear,
+// src/imagew-main.c:669-765, in the table form of kernels.cuh:candidates_table/quantise for levels whose stored
+// code is the level index).  `q` is the FP32 guess of the level; the true one is found by stepping from it.
+template <int FAM>
+__device__ __noinline__ int exact8_v2(const double *thr, int top, double s, int q, float t, uint32_t draw) {
+  s = s < 0.0 ? 0.0 : (s > 1.0 ? 1.0 : s);
+  if (s > 0.999999999) return top;
+  q = max(0, min(q, top));
+  while (q < top && thr[q + 1] <= s) q++;
+  while (q > 0 && thr[q] > s) q--;
+  if (q >= top) return top;
+  const double d_floor = __dsub_rn(s, thr[q]), d_ceil = __dsub_rn(thr[q + 1], s);
+  if (FAM == 0) return d_ceil <= d_floor ? q + 1 : q;
+  const double frac = __ddiv_rn(d_floor, __dadd_rn(d_floor, d_ceil));
+  const double th = FAM == 1 ? (double)t : __ddiv_rn((double)draw, (double)0xffffffffu);
+  return frac >= th ? q + 1 : q;
+}
+
+template <int EPI>
+__device__ __forceinline__ int quantise8_v2(const unsigned char *tab, float margin, int top, float t, double s, uint32_t draw) {
+  const float4 *e4_s = (const float4 *)tab;
+  const uint16_t *hint_s = (const uint16_t *)(tab + IWB2_TAB_HINT);
+  const double *thr_s = (const double *)(tab + IWB2_TAB_THR);
+  if (EPI == 4) {
+    // random dither compares against draw/0xffffffff which can be exactly 0 or 1: keep the reference's exact
+    // end cases (src/imagew-main.c:618-621, :684-685)
+    if (!(s > 0.0)) return 0;
+    if (s > 0.999999999) return top;
+  }
+  const float sf = __saturatef((float)s);                       // NaN/negative -> 0, > 1 -> 1
+  const int b = (int)(sf * (float)IWB2_NHINT);
+  const int q0 = hint_s[b];
+  const float4 e = e4_s[q0];
+  const bool up = sf >= e.z;
+  const float lo = up ? e.z : e.x, inv = up ? e.w : e.y;
+  const int q = q0 + (up ? 1 : 0);
+  const float fr = (sf - lo) * inv;
+  const float d = fr - t;
+  // random thresholds reach 0 and 1: a sample within the margin of a level boundary also goes the exact way
+  const bool sure = EPI == 4 ? (fabsf(d) > margin && fr > margin && fr < 1.0f - margin) : fabsf(d) > margin;
+  if (sure) return q + (d >= 0.0f ? 1 : 0);
+  return exact8_v2<EPI == 1 ? 0 : (EPI == 3 ? 1 : 3)>(thr_s, top, s, q, t, draw);
+}
+
+// Write the warp's staged output bytes: `nrows` rows of `nbytes` bytes, coalesced per row (4-byte words when the
+// destination allows).  Out of line: it runs once per ~40 pixels and would otherwise be inlined into every phase.
+static __device__ __noinline__ void h2_flush(const unsigned char *ost, uint8_t *dst, size_t bpr, int nbytes, int nrows, bool walign, int lane) {
+  __syncwarp();
+  if (walign && (nbytes & 3) == 0) {
+    if (lane * 4 < nbytes) {
+      for (int k = 0; k < nrows; k++)
+        *reinterpret_cast<unsigned *>(dst + (size_t)k * bpr + lane * 4) = *reinterpret_cast<const unsigned *>(ost + k * IWB2_OST_PITCH + lane * 4);
+    }
+  } else {
+    for (int k = 0; k < nrows; k++)
+      for (int b = lane; b < nbytes; b += 32) dst[(size_t)k * bpr + b] = ost[k * IWB2_OST_PITCH + b];
+  }
+  __syncwarp();
+}
+
+template <int S, int STEP, int NCH, int EPI>
+__global__ void __launch_bounds__(32 * IWB2_H_WARPS) iwb_h2(const H2Params p) {
+  constexpr int SS = (S + 1) & ~1;
+  constexpr int KP = IWB2_H_KP, NST = IWB2_H_NST;
+  constexpr int STAGE = KP * NCH * 128 + KP * SS * 8;
+  constexpr int GU = STEP > 0 ? S * STEP : 2, NSTU = IWB2_U_NST;
+  constexpr int STAGE_U = (GU * NCH * 128 + GU * SS * 8 + 127) & ~127;
+  constexpr int RING = NST * STAGE > NSTU * STAGE_U ? NST * STAGE : NSTU * STAGE_U;
+  constexpr int WARP_BYTES = (RING + 32 * IWB2_OST_PITCH + 8 * 8 + 127) & ~127;
+  constexpr int FU = NCH == 3 ? 40 : 128;                       // pixels per flush (FU * NCH bytes <= 128, multiple of 4)
+  static_assert(KP >= 2 && NST >= 3 && GU >= 2 && NSTU >= 2, "pipeline depth");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int xo0, xo1;
+  bool uni;
+  s2_decode_part(p.part, blockIdx.x, 0, p.out_w, &xo0, &xo1, &uni);
+  if (STEP == 0) uni = false;
+  const int ntab = p.same_tables ? 1 : NCH;
+
+  unsigned char *wbase = smem_raw + (size_t)warp * WARP_BYTES;
+  unsigned char *ost = wbase + RING;                            // [32 rows][pitch]
+  const unsigned bar0 = s2_addr(wbase + RING + 32 * IWB2_OST_PITCH);
+  unsigned char *tab_s = smem_raw + (size_t)IWB2_H_WARPS * WARP_BYTES;          // [ntab][IWB2_TAB_BYTES]
+  float *ord_s = (float *)(tab_s + (size_t)ntab * IWB2_TAB_BYTES);              // [64]
+  uint64_t *tbar = (uint64_t *)(ord_s + 64);
+  int *last_s = (int *)(tbar + 2);                                              // general path: [nout]
+
+  const int grp = blockIdx.y * IWB2_H_WARPS + warp;             // row group of this warp
+  const int jb = p.row_lo + grp * 32;
+  const bool active = jb < p.row_hi;
+  const int y = jb + lane;
+  const unsigned ring0 = s2_addr(wbase);
+  const float *gbase = p.inter + (size_t)grp * p.ncols_pad * 32;
+
+  int b0 = 0, nb = 0, xb = xo0, nout = 0, nstg = 0;             // general-path geometry
+  int og0 = 0, ncyc = 0, B0 = 0;                                // uniform-path geometry (see the vertical kernel)
+  if (uni) {
+    og0 = s2_floor_div(xo0 - (S - 1), S) * S;
+    ncyc = (xo1 - og0 + S - 1) / S;
+    B0 = p.part.u_ref_last + STEP * (og0 - p.part.u_ref_o) - STEP + 1;
+  } else {
+    b0 = p.sc.first[xo0];
+    nb = p.sc.last[xo1 - 1] - b0 + 1;
+    while (xb > 0 && p.sc.last[xb - 1] >= b0) xb--;             // first output still open at b0
+    nout = xo1 - xb;
+    nstg = (nb + KP - 1) / KP;
+  }
+  // stage n = KP (GU) pixel columns of this row group -- one contiguous block of the blocked transposed
+  // intermediate, which is padded on both sides so that a stage may start before column 0 or end after the last
+  // one (those columns meet zero weights) -- + the schedule rows of weights
+  auto fill = [&](int n, int slot) {
+    if (s2_elect()) {
+      const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE;
+      s2_mbar_expect(bar, KP * NCH * 128 + KP * SS * 8);
+      s2_bulk_g2s(dst, gbase + (ptrdiff_t)(b0 + n * KP) * NCH * 32, KP * NCH * 128, bar);
+      s2_bulk_g2s(dst + KP * NCH * 128, p.sc.w + (ptrdiff_t)(b0 + n * KP) * SS, KP * SS * 8, bar);
+    }
+  };
+  auto fill_u = [&](int n, int slot) {
+    if (s2_elect()) {
+      const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE_U;
+      s2_mbar_expect(bar, GU * NCH * 128 + GU * SS * 8);
+      s2_bulk_g2s(dst, gbase + (ptrdiff_t)(B0 + n * GU) * NCH * 32, GU * NCH * 128, bar);
+      s2_bulk_g2s(dst + GU * NCH * 128, p.sc.w + (ptrdiff_t)(B0 + n * GU) * SS, GU * SS * 8, bar);
+    }
+  };
+  // prologue: start this warp's pipeline and the (asynchronous) copy of the decision tables, then the small loops
+  if (active) {
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < 8; s++) s2_mbar_init(bar0 + 8 * s, 1);
+      s2_fence_async();
+    }
+    __syncwarp();
+    if (uni) {
+#pragma unroll
+      for (int s = 0; s < NSTU; s++)
+        if (s <= ncyc) fill_u(s, s);
+    } else {
+#pragma unroll
+      for (int s = 0; s < NST; s++)
+        if (s < nstg) fill(s, s);
+    }
+  }
+  if (threadIdx.x == 0) {
+    const unsigned tb = s2_addr(tbar);
+    s2_mbar_init(tb, 1);
+    s2_fence_async();
+    s2_mbar_expect(tb, (unsigned)ntab * IWB2_TAB_BYTES);
+    for (int k = 0; k < ntab; k++) s2_bulk_g2s(s2_addr(tab_s + (size_t)k * IWB2_TAB_BYTES), p.q[k].blob, IWB2_TAB_BYTES, tb);
+  }
+  for (int i = threadIdx.x; i < 64; i += blockDim.x)
+    ord_s[i] = ((float)iwb2_ord[(p.ch[0].dsubtype == 1 ? 64 : 0) + i] + 0.5f) / 64.0f;   // exact in float
+  if (!uni)
+    for (int i = threadIdx.x; i < nout; i += blockDim.x) last_s[i] = p.sc.last[xb + i] - b0;
+  __syncthreads();
+  if (!active) return;
+  s2_mbar_wait(s2_addr(tbar), 0);
+
+  double acc[S][NCH], prod[S][NCH];
+#pragma unroll
+  for (int s = 0; s < S; s++)
+#pragma unroll
+    for (int c = 0; c < NCH; c++) { acc[s][c] = 0.0; prod[s][c] = 0.0; }
+
+  // random dither: this thread's draws are consecutive along its row, one per output pixel and channel
+  uint64_t rng[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    rng[c] = 0;
+    if (EPI == 4 && y < p.row_hi) {
+      uint64_t t = p.ch[c].prng_t1;
+      const uint64_t n = (uint64_t)y * (uint64_t)p.out_w + (uint64_t)xo0;
+      if (n) { if (t >= IWB_PRNG_P) t -= IWB_PRNG_P; t = iwb_prng_jump(t, n, p.jump); }
+      rng[c] = t;
+    }
+  }
+  const float *ord_t = ord_s + (y & 7) * 8;                     // this row's eight ordered-dither thresholds
+
+  // one input pixel column: `nxt` is the shared-memory address of the next column's first channel for this lane
+  auto taps = [&](double (&vc)[NCH], unsigned nxt, unsigned wrow) {
+    double2 w[SS / 2];
+#pragma unroll
+    for (int s2 = 0; s2 < SS / 2; s2++) w[s2] = s2_ldsw(wrow + 16 * s2);
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+#pragma unroll
+      for (int s = 0; s < S; s++) {
+        if (IWB2_DEFER) {
+          acc[s][c] = __dadd_rn(acc[s][c], prod[s][c]);
+          prod[s][c] = __dmul_rn(vc[c], (s & 1) ? w[s >> 1].y : w[s >> 1].x);
+        } else {
+          acc[s][c] = __dadd_rn(acc[s][c], __dmul_rn(vc[c], (s & 1) ? w[s >> 1].y : w[s >> 1].x));
+        }
+      }
+      vc[c] = (double)s2_ldsf(nxt + 128 * c);                   // next column, in place
+    }
+  };
+
+  // output staging: the warp's 32 rows x up to FU pixels, flushed as 4-byte words (coalesced per row)
+  int staged_from = xo0;
+  unsigned char *ost_t = ost + lane * IWB2_OST_PITCH;
+  const bool walign = (((uintptr_t)p.out.pix | p.out.bpr) & 3) == 0;
+  auto flush = [&](int upto) {
+    h2_flush(ost, p.out.pix + (size_t)(jb - p.out.row_origin) * p.out.bpr + (size_t)staged_from * NCH, p.out.bpr,
+             (upto - staged_from) * NCH, min(32, p.row_hi - jb), walign, lane);
+    staged_from = upto;
+  };
+  // slot k is complete: add its pending products, quantise + dither, stage the bytes, restart the slot
+  auto finish = [&](int k, int xo) {
+#pragma unroll
+    for (int c = 0; c < NCH; c++) if (IWB2_DEFER) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
+    if (xo >= xo0 && xo < xo1) {
+      if (xo - staged_from >= FU) flush(xo);
+      unsigned char *dstb = ost_t + (xo - staged_from) * NCH;
+      float t = 0.5f;
+      if (EPI == 3) t = ord_t[xo & 7];
+#pragma unroll
+      for (int c = 0; c < NCH; c++) {
+        uint32_t draw = 0;
+        if (EPI == 4) {
+          draw = iwb_prng_draw_of(rng[c]);
+          rng[c] = iwb_prng_step(rng[c]);
+          t = (float)draw * (1.0f / 4294967295.0f);
+        }
+        const int tb = p.same_tables ? 0 : c;
+        dstb[c] = (uint8_t)quantise8_v2<EPI>(tab_s + (size_t)tb * IWB2_TAB_BYTES, p.q[tb].margin, p.q[tb].top, t, acc[k][c], draw);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; c++) acc[k][c] = 0.0;
+  };
+
+  if (STEP > 0 && uni) {
+    // ---- uniform path --------------------------------------------------------------------------------
+    int slot = 0;
+    unsigned par = 0;
+    s2_mbar_wait(bar0, 0);
+    double vc[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) vc[c] = (double)s2_ldsf(ring0 + lane * 4 + 128 * c);   // column 0
+    for (int cyc = 0; cyc < ncyc; cyc++) {
+      const int nslot = slot + 1 == NSTU ? 0 : slot + 1;
+      const unsigned npar = nslot == 0 ? par ^ 1 : par;
+      const unsigned sb = ring0 + slot * STAGE_U + lane * 4, sbn = ring0 + nslot * STAGE_U + lane * 4;
+      const unsigned wb = ring0 + slot * STAGE_U + GU * NCH * 128;
+      const int og = og0 + cyc * S;
+#pragma unroll
+      for (int r = 0; r < GU; r++) {
+        if (r == GU - 1) s2_mbar_wait(bar0 + 8 * nslot, npar);  // the last column prefetches from the next stage
+        taps(vc, r + 1 < GU ? sb + (r + 1) * NCH * 128 : sbn, wb + r * SS * 8);
+        if ((r + 1) % STEP == 0) finish((r + 1) / STEP - 1, og + (r + 1) / STEP - 1);
+      }
+      __syncwarp();
+      if (cyc + NSTU <= ncyc) fill_u(cyc + NSTU, slot);
+      slot = nslot;
+      par = npar;
+    }
+    flush(xo1);
+    return;
+  }
+
+  // ---- general path ------------------------------------------------------------------------------------
+  // read position (samples, one pixel ahead of the arithmetic) and weights position, as in the vertical kernel
+  int ld_stage = 0, ld_slot = 0, w_slot = 0;
+  unsigned parity = 0;
+  s2_mbar_wait(bar0, 0);
+  unsigned pin = ring0 + lane * 4;
+  unsigned pin_end = pin + KP * NCH * 128;
+  unsigned pw = ring0 + KP * NCH * 128;
+  unsigned pw_end = pw + KP * SS * 8;
+  auto advance_load = [&]() {
+    __syncwarp();
+    if (ld_stage >= 1 && ld_stage - 1 + NST < nstg) fill(ld_stage - 1 + NST, ld_slot == 0 ? NST - 1 : ld_slot - 1);
+    ld_stage++;
+    if (++ld_slot == NST) { ld_slot = 0; parity ^= 1; }
+    if (ld_stage < nstg) s2_mbar_wait(bar0 + 8 * ld_slot, parity);
+    pin = ring0 + ld_slot * STAGE + lane * 4;
+    pin_end = pin + KP * NCH * 128;
+  };
+  double vc[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; c++) vc[c] = (double)s2_ldsf(pin + 128 * c);       // pixel column 0
+  pin += NCH * 128;
+  if (pin == pin_end) advance_load();
+  int i = 0;                                                    // pixel column being consumed (relative to b0)
+  auto col_step = [&]() {
+    taps(vc, pin, pw);
+    pin += NCH * 128;
+    if (pin == pin_end) advance_load();
+    pw += SS * 8;
+    if (pw == pw_end) {
+      if (++w_slot == NST) w_slot = 0;
+      pw = ring0 + w_slot * STAGE + KP * NCH * 128;
+      pw_end = pw + KP * SS * 8;
+    }
+    i++;
+  };
+  for (int og = xb - (xb % S); og < xo1; og += S) {
+#pragma unroll
+    for (int k = 0; k < S; k++) {
+      const int o = og + k;
+      if (o >= xb && o < xo1) {                                 // warp-uniform
+        const int iend = last_s[o - xb];
+        while (i <= iend) col_step();
+        finish(k, o);
+      }
+    }
+  }
+  flush(xo1);
+}

@@ -1,0 +1,141 @@
+// stream2_host.cuh -- host-side planning shared by the stream2 translation units: tensor maps, occupancy, and the
+// split of a launch into uniform and general parts (see Part2 in stream2.cuh).
+#pragma once
+#include <algorithm>
+#include <cstring>
+
+#include "stream2_dev.cuh"
+
+// (slots, uniform step) pairs the kernels are instantiated for; a cycle is S*STEP inputs (4..IWB2_MAX_GU)
+#ifdef IWB_QUICK
+#define IWB2_UNIFORM_PAIRS(X) X(6, 2)
+#define IWB2_GENERAL_S(X) X(6)
+#else
+#define IWB2_UNIFORM_PAIRS(X) \
+  X(2, 2) X(3, 2) X(4, 2) X(5, 2) X(6, 2) X(8, 2) X(2, 3) X(3, 3) X(4, 3) X(5, 3) X(2, 4) X(3, 4) X(4, 4)
+#define IWB2_GENERAL_S(X) X(2) X(3) X(4) X(5) X(6) X(8)
+#endif
+
+static inline bool iwb2_pair_built(int S, int step) {
+#define X(a, b) if (S == a && step == b) return true;
+  IWB2_UNIFORM_PAIRS(X)
+#undef X
+  return false;
+}
+static inline bool iwb2_s_built(int S) {
+#define X(a) if (S == a) return true;
+  IWB2_GENERAL_S(X)
+#undef X
+  return false;
+}
+
+typedef CUresult (*iwb2_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline iwb2_encode_fn iwb2_tensor_map_encoder() {        // driver entry point without linking libcuda
+  static iwb2_encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (iwb2_encode_fn)f;
+  }
+  return fn;
+}
+
+static inline int iwb2_sm_count() {
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!sms[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = v > 0 ? v : 148;
+  }
+  return sms[dev];
+}
+
+// Resident CTAs per SM of a kernel at a given dynamic shared-memory size (also raises the kernel's limit).
+template <class K>
+static int iwb2_ctas_per_sm(K kernel, int threads, size_t smem) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess) n = 1;
+  return n < 1 ? 1 : n;
+}
+
+// Split outputs [lo, hi) into parts.  `last` = host copy of the schedule's window ends, `base`/`align`: part
+// boundaries must be base + k*align, `want` = how many parts make one full wave.  A uniform range needs a constant
+// integer step between consecutive window ends (the weights themselves come from the schedule table: they are
+// not bitwise periodic in general).  Returns the uniform step (0: none).
+static inline int iwb2_plan_parts(const int *last, int n_out, int lo, int hi, int base, int align, int S, int want, int len_override,
+                                  int g_min, int step_wanted, Part2 *pt, int *nparts) {
+  auto up = [&](int v) { return base + ((v - base + align - 1) / align) * align; };
+  auto down = [&](int v) { return base + ((v - base) / align) * align; };
+  int step = 0, a = lo, b = lo;
+  const int mid = lo + (hi - lo) / 2;
+  if (step_wanted > 0 && mid + 1 < n_out && mid >= 0 && last[mid + 1] - last[mid] == step_wanted && iwb2_pair_built(S, step_wanted)) {
+    step = step_wanted;
+    a = mid;
+    while (a - 1 >= 0 && last[a] - last[a - 1] == step) a--;
+    b = mid + 1;
+    while (b < n_out && last[b] - last[b - 1] == step) b++;
+    pt->u_ref_o = mid;                                           // any output of the range anchors the progression
+    pt->u_ref_last = last[mid];
+  }
+  int u_lo = lo, u_hi = lo;
+  if (step) {
+    u_lo = up(std::max(lo, a));
+    u_hi = std::min(hi, b);
+    if (u_hi < hi) u_hi = down(u_hi);
+    if (u_hi - u_lo < std::max(4 * align, 4 * S)) { step = 0; u_lo = u_hi = lo; }
+  }
+  want = std::max(1, want);
+  if (!step) { pt->u_ref_o = 0; pt->u_ref_last = 0; }
+  if (step) {
+    // what is left outside the uniform range: parts of at least g_min outputs, at most about a tenth of the wave
+    const int rest = (u_lo - lo) + (hi - u_hi);
+    int glen = (rest + std::max(1, want / 10) - 1) / std::max(1, want / 10);
+    pt->g_len = std::max(std::max(g_min, align), ((glen + align - 1) / align) * align);
+    const int n_g = (u_lo - lo + pt->g_len - 1) / pt->g_len + (hi - u_hi + pt->g_len - 1) / pt->g_len;
+    const int n_u_want = std::max(1, want - n_g);
+    int len = len_override > 0 ? len_override : (u_hi - u_lo + n_u_want - 1) / n_u_want;
+    len = std::max(align, ((len + align - 1) / align) * align);
+    pt->u_lo = u_lo; pt->u_hi = u_hi; pt->u_len = len;
+    pt->n_u = (u_hi - u_lo + len - 1) / len;
+    *nparts = pt->n_u + n_g;
+  } else {
+    int len = len_override > 0 ? len_override : (hi - lo + want - 1) / want;
+    len = std::max(std::max(g_min, align), ((len + align - 1) / align) * align);
+    pt->n_u = 0; pt->u_lo = pt->u_hi = lo; pt->u_len = align;
+    pt->g_len = len;
+    *nparts = (hi - lo + len - 1) / len;
+  }
+  return step;
+}
+
+static inline size_t iwb2_v_smem(int S, int step, int nout) {
+  const int SS = (S + 1) & ~1;
+  const size_t stage = (size_t)IWB2_V_G * 128 + (size_t)IWB2_V_G * SS * 8;
+  const int gu = step > 0 ? S * step : 4;
+  const size_t stage_u = ((size_t)gu * 128 + (size_t)gu * SS * 8 + 127) & ~(size_t)127;
+  const size_t ring = std::max((size_t)IWB2_V_NST * stage, (size_t)IWB2_U_NST * stage_u);
+  const size_t warp_bytes = (ring + 8 * 4 * 32 * 4 + 8 * 8 + 127) & ~(size_t)127;
+  return 256 * 16 * 8 + IWB2_V_WARPS * warp_bytes + (size_t)nout * 4 + 16;
+}
+static inline size_t iwb2_h_smem(int S, int step, int nch, int ntab, int nout) {
+  const int SS = (S + 1) & ~1;
+  const size_t stage = (size_t)IWB2_H_KP * nch * 128 + (size_t)IWB2_H_KP * SS * 8;
+  const int gu = step > 0 ? S * step : 2;
+  const size_t stage_u = ((size_t)gu * nch * 128 + (size_t)gu * SS * 8 + 127) & ~(size_t)127;
+  const size_t ring = std::max((size_t)IWB2_H_NST * stage, (size_t)IWB2_U_NST * stage_u);
+  const size_t warp_bytes = (ring + 32 * IWB2_OST_PITCH + 8 * 8 + 127) & ~(size_t)127;
+  return IWB2_H_WARPS * warp_bytes + (size_t)ntab * IWB2_TAB_BYTES + 64 * 4 + 16 + (size_t)nout * 4 + 16;
+}
+
+bool iwb2_run_h_e1(const H2Job &job, cudaStream_t st);
+bool iwb2_run_h_e3(const H2Job &job, cudaStream_t st);
+bool iwb2_run_h_e4(const H2Job &job, cudaStream_t st);
