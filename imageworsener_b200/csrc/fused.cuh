@@ -98,7 +98,6 @@ struct FastPlan {
   int strip2 = 0, seg2 = 0;                        // 0: sized per launch to one wave of CTAs
   int uniform = 1;
   int ncols_pad = 0;
-  size_t inter_pad = 0;                            // floats of padding in front of the intermediate
 };
 
 #if !defined(IWB_EMU)

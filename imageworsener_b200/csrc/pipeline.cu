@@ -780,12 +780,12 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
 static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const DevOutput &out, int r0, int r1,
                       iwb_stream stream) {
   if (!f->interT) {
-    // gen 2 reads whole stages: up to IWB2_WPAD pixel columns before the first / after the last column of a row group
-    f->inter_pad = (size_t)IWB2_WPAD * 4 * 32;
-    const size_t bytes = ((size_t)std::max(job->in_w * f->nch, f->ncols_pad) * f->pitch_j + 2 * f->inter_pad) * sizeof(float);
+    // (+4 floats per row: gen 2 stores column c at float c + shift; zeroed once so the 0..3 floats in front of column
+    // 0 are finite -- they meet zero weights)
+    const size_t bytes = (size_t)(std::max(job->in_w * f->nch, f->ncols_pad) + 4) * f->pitch_j * sizeof(float);
     f->interT = (float *)job->scratch(bytes);
     if (!f->interT) return false;
-    cudaMemsetAsync(f->interT, 0, bytes, stream);   // rows past the end of a partial row group are read (and ignored)
+    cudaMemsetAsync(f->interT, 0, bytes, stream);
   }
   const int nch = f->nch;
   // second-generation kernels: TMA needs 16-byte aligned rows
@@ -793,23 +793,25 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
   if (f->v2 && in.bpr % 16 == 0 && ((uintptr_t)src0 & 15) == 0) {
     for (int c0 = r0; c0 < r1; c0 += f->chunk_rows) {
       const int c1 = std::min(r1, c0 + f->chunk_rows);
+      H2Job hj{};
+      H2Params &hp = hj.p;
+      hp.inter = f->interT; hp.pitch = f->ncols_pad + 4; hp.ncols = job->in_w * nch; hp.row_lo = c0; hp.row_hi = c1; hp.sc = *f->s2h;
+      hp.out_w = out.width; hp.out = out; hp.same_tables = f->same_tables; hp.jump = job->d_jump;
+      for (int p = 0; p < 4; p++) { hp.ch[p] = job->cout[p < nch ? p : 0]; hp.q[p] = f->q2[p < nch ? p : 0]; }
+      hj.S = f->SH; hj.nch = nch; hj.epi = f->epi; hj.last_host = f->hlast.data(); hj.seg_override = f->seg2; hj.allow_uniform = f->uniform;
+      hp.sh = 0;
+      hp.sh = iwb2_h_shift(hj);            // where the horizontal pass wants column 0 (16-byte aligned TMA tiles)
       V2Job vj{};
       V2Params &vp = vj.p;
       vp.src = src0; vp.bpr = in.bpr; vp.ncols = job->in_w * nch; vp.lut = f->lut; vp.sc = *f->s2v;
       vp.tm_row0 = f->vfirst[c0]; vp.tm_rows = f->vlast[c1 - 1] - f->vfirst[c0] + 1;
-      vp.inter = f->interT + f->inter_pad; vp.ncols_pad = f->ncols_pad; vp.row_base = c0; vp.row_lo = c0; vp.row_hi = c1;
+      vp.inter = f->interT; vp.pitch = f->ncols_pad + 4; vp.sh = hp.sh; vp.row_base = c0; vp.row_lo = c0; vp.row_hi = c1;
       vj.S = f->SV; vj.last_host = f->vlast.data(); vj.strip_override = f->strip2; vj.allow_uniform = f->uniform;
       {
         prof_scope ps(job, 5, stream);
         if (!iwb2_run_v(vj, (cudaStream_t)stream)) return fail(job, "fast path: no vertical kernel variant (gen 2)");
         g_launches++;
       }
-      H2Job hj{};
-      H2Params &hp = hj.p;
-      hp.inter = f->interT + f->inter_pad; hp.ncols_pad = f->ncols_pad; hp.row_lo = c0; hp.row_hi = c1; hp.sc = *f->s2h;
-      hp.out_w = out.width; hp.out = out; hp.same_tables = f->same_tables; hp.jump = job->d_jump;
-      for (int p = 0; p < 4; p++) { hp.ch[p] = job->cout[p < nch ? p : 0]; hp.q[p] = f->q2[p < nch ? p : 0]; }
-      hj.S = f->SH; hj.nch = nch; hj.epi = f->epi; hj.last_host = f->hlast.data(); hj.seg_override = f->seg2; hj.allow_uniform = f->uniform;
       {
         prof_scope ps(job, 1, stream);
         if (!iwb2_run_h(hj, (cudaStream_t)stream)) return fail(job, "fast path: no horizontal kernel variant (gen 2)");

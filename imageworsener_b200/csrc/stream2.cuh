@@ -6,13 +6,14 @@
 //
 //   * each warp owns a ring of stages in shared memory; one elected lane posts the byte count on the stage's
 //     mbarrier and issues the copies (SASS UTMALDG / UBLKCP): a 2-D tensor tile of G input rows x 128 bytes + the G
-//     schedule rows of weights (vertical), or KP pixel columns x 32 rows of the FP32 intermediate as ONE
-//     contiguous block + KP schedule rows (horizontal).  No thread ever issues a per-sample global load, there is
+//     schedule rows of weights (vertical), or a tile of KP pixel columns x 32 rows of the FP32 intermediate + KP
+//     schedule rows (horizontal).  No thread ever issues a per-sample global load, there is
 //     no __syncthreads in the steady state, and shared memory does not grow with the strip / segment length;
-//   * the FP32 intermediate is stored "blocked transposed": inter[row group of 32][column][32 rows], so the
-//     horizontal kernel (lanes = 32 rows, schedule warp-uniform) gets a column range of its row group with one
-//     contiguous bulk copy and reads it with conflict-free LDS.32 at immediate offsets, while the vertical
-//     kernel still writes whole 32-byte sectors (8 finished rows of a column);
+//   * the FP32 intermediate is plain row-major: the vertical kernel stores each finished row of a warp as one
+//     coalesced 512-byte segment straight from registers; the horizontal kernel (lanes = 32 rows, so that the
+//     schedule is warp-uniform) gets [32 rows][columns] tiles by 2-D TMA and reads its row 16 bytes at a time --
+//     with a tile pitch of an odd number of 16-byte chunks that access is bank-conflict free, i.e. the
+//     transposition between the two passes costs nothing;
 //   * where the schedule is regular (integer reduction factors away from the border) a whole cycle of S outputs
 //     is straight-line code (stream2_dev.cuh); elsewhere per-output trip counts come from the schedule tables;
 //   * the 8-bit epilogue is branch-free in the common case: clamp by saturation, bucket -> level by one u16 and
@@ -42,7 +43,7 @@
 #define IWB2_H_KP 4              // general path: pixel columns per stage
 #endif
 #ifndef IWB2_H_NST
-#define IWB2_H_NST 4
+#define IWB2_H_NST 3
 #endif
 #ifndef IWB2_U_NST
 #define IWB2_U_NST 2             // uniform path: stages (one cycle of S outputs each)
@@ -50,7 +51,9 @@
 #ifndef IWB2_DEFER
 #define IWB2_DEFER 1             // deferred adds (stream2_dev.cuh); 0 trades them for registers / occupancy
 #endif
-#define IWB2_OST_PITCH 132       // bytes per output staging row (33 words: lane-private banks)
+#ifndef IWB2_OST_PITCH
+#define IWB2_OST_PITCH 100       // bytes per output staging row (25 words, odd: lane-private banks); <= 96 bytes staged
+#endif
 #define IWB2_NHINT 4096
 #define IWB2_WPAD 64             // schedule rows of zero weights before row 0 and after the last row
 #define IWB2_MAX_GU 16           // longest uniform cycle (inputs) the kernels are built for
@@ -90,16 +93,17 @@ struct V2Params {
   int ncols;                     // byte columns (= in_w * channels)
   const double *lut;             // [256] code -> linear
   Sched2 sc;
-  float *inter;                  // blocked transposed intermediate
-  int ncols_pad;                 // columns per row group in `inter`
+  float *inter;                  // row-major FP32 intermediate
+  int pitch;                     // floats per row of `inter` (multiple of 4)
+  int sh;                        // column c is stored at float index c + sh (0..3, see iwb2_h_shift)
   int row_base;                  // output row stored as row 0 of `inter`
   int row_lo, row_hi;            // output rows of this launch
-  Part2 part;                    // strips (lengths are multiples of 8 rows counted from row_base)
+  Part2 part;                    // strips
 };
 
 struct H2Params {
-  const float *inter;
-  int ncols_pad;
+  const float *inter;            // row-major FP32 intermediate (read through a tensor map built at launch)
+  int pitch, ncols, sh;          // floats per row of `inter`; valid floats per row (= in_w * channels); column shift
   int row_lo, row_hi;            // output rows of this launch; row_lo is row 0 of `inter`
   Sched2 sc;                     // in pixels
   Part2 part;                    // segments of output pixels (lengths are multiples of 4)
@@ -131,6 +135,7 @@ struct H2Job {
 bool iwb2_tensor_maps_available();
 bool iwb2_run_v(const V2Job &job, cudaStream_t st);   // false: no kernel variant / launch problem
 bool iwb2_run_h(const H2Job &job, cudaStream_t st);
+int iwb2_h_shift(const H2Job &job);                    // the column shift (0..3) this horizontal launch wants from the vertical one
 bool iwb2_supported(int SV, int SH, int nch, int epi);
 
 #endif  // !IWB_EMU

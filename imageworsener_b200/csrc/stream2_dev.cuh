@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
   constexpr int GU = STEP > 0 ? S * STEP : 4, NSTU = IWB2_U_NST;   // uniform path: one cycle per stage
   constexpr int STAGE_U = (GU * 128 + GU * SS * 8 + 127) & ~127;
   constexpr int RING = NST * STAGE > NSTU * STAGE_U ? NST * STAGE : NSTU * STAGE_U;
-  constexpr int WARP_BYTES = (RING + 8 * 4 * 32 * 4 + 8 * 8 + 127) & ~127;   // TMA tiles land on 128-byte boundaries
+  constexpr int WARP_BYTES = (RING + 8 * 8 + 127) & ~127;       // TMA tiles land on 128-byte boundaries
   static_assert(G >= 4 && NST >= 3 && GU >= 4 && NSTU >= 2, "pipeline depth");
   static_assert((STAGE % 128) == 0 && (STAGE_U % 128) == 0, "stage alignment");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -117,8 +117,7 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
 
   double *lut_s = (double *)smem_raw;                           // [256][16]
   unsigned char *wbase = smem_raw + 256 * 16 * 8 + (size_t)warp * WARP_BYTES;
-  float *tbuf = (float *)(wbase + RING);                        // [8 rows][4 cols][32 lanes]
-  const unsigned bar0 = s2_addr(wbase + RING + 8 * 4 * 32 * 4);
+  const unsigned bar0 = s2_addr(wbase + RING);
   int *last_s = (int *)(smem_raw + 256 * 16 * 8 + (size_t)IWB2_V_WARPS * WARP_BYTES);   // general path: [nout]
   const int wcol0 = (blockIdx.x * IWB2_V_WARPS + warp) * 128;
   const bool active = wcol0 < p.ncols;
@@ -215,34 +214,35 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
       vc[c] = lookup1(xn, c);
     }
   };
-  // slot k is complete: add its pending products, hand the row to the transposing store, restart the slot
+  // slot k is complete: add its pending products, round to FP32 (reference: src/imagew-main.c:905-912) and store the
+  // warp's 128 columns of this intermediate row as one coalesced 512-byte segment; restart the slot
   auto finish = [&](int k, int o) {
 #pragma unroll
     for (int c = 0; c < 4; c++) if (IWB2_DEFER) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
     if (o >= o0 && o < o1) {
-      const int orel = o - p.row_base, tb = orel & 7;
-#pragma unroll
-      for (int c = 0; c < 4; c++) tbuf[(tb * 4 + c) * 32 + lane] = (float)acc[k][c];
-      if (tb == 7 || o == o1 - 1) {                             // 8 consecutive rows of each column: one 32-byte sector
-        const int base = orel - tb, cnt = tb + 1;
-        float *dst0 = p.inter + ((size_t)(base >> 5) * p.ncols_pad + col0) * 32 + (base & 31);
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          if (full || col0 + c < p.ncols) {
-            float g[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) g[r] = tbuf[(r * 4 + c) * 32 + lane];
-            float *dst = dst0 + c * 32;
-            if (cnt == 8) {
-              *reinterpret_cast<float4 *>(dst) = make_float4(g[0], g[1], g[2], g[3]);
-              *reinterpret_cast<float4 *>(dst + 4) = make_float4(g[4], g[5], g[6], g[7]);
-            } else {
-#pragma unroll
-              for (int r = 0; r < 8; r++)
-                if (r < cnt) dst[r] = g[r];
-            }
-          }
+      // column c is stored at float index c + sh: the shift (0..3, chosen per launch) puts the horizontal kernel's
+      // tiles on 16-byte boundaries, which its TMA loads need; here it only splits the 16-byte store
+      float *dst = p.inter + (size_t)(o - p.row_base) * p.pitch + p.sh + col0;
+      if (full) {
+        const float f0 = (float)acc[k][0], f1 = (float)acc[k][1], f2 = (float)acc[k][2], f3 = (float)acc[k][3];
+        if (p.sh == 0) {
+          *reinterpret_cast<float4 *>(dst) = make_float4(f0, f1, f2, f3);
+        } else if (p.sh == 2) {
+          *reinterpret_cast<float2 *>(dst) = make_float2(f0, f1);
+          *reinterpret_cast<float2 *>(dst + 2) = make_float2(f2, f3);
+        } else if (p.sh == 1) {
+          dst[0] = f0;
+          *reinterpret_cast<float2 *>(dst + 1) = make_float2(f1, f2);
+          dst[3] = f3;
+        } else {
+          *reinterpret_cast<float2 *>(dst + 1) = make_float2(f1, f2);   // (sh == 3: dst + 1 is 8-byte aligned)
+          dst[0] = f0;
+          dst[3] = f3;
         }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+          if (col0 + c < p.ncols) dst[c] = (float)acc[k][c];
       }
     }
 #pragma unroll
@@ -412,16 +412,26 @@ static __device__ __noinline__ void h2_flush(const unsigned char *ost, uint8_t *
   __syncwarp();
 }
 
+// Shared-memory pitch (floats) of a tile of `k` floats per row: a multiple of 4 with an odd number of 16-byte
+// chunks, so that 32 lanes reading 16 bytes each from 32 different rows touch every bank exactly once per
+// quarter-warp (the row-major intermediate is transposed for free by this access pattern).
+__host__ __device__ constexpr int iwb2_tile_pitch(int k) { return (((k + 3) / 4) | 1) * 4; }
+
 template <int S, int STEP, int NCH, int EPI>
-__global__ void __launch_bounds__(32 * IWB2_H_WARPS) iwb_h2(const H2Params p) {
+__global__ void __launch_bounds__(32 * IWB2_H_WARPS)
+    iwb_h2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_u, const H2Params p) {
   constexpr int SS = (S + 1) & ~1;
   constexpr int KP = IWB2_H_KP, NST = IWB2_H_NST;
-  constexpr int STAGE = KP * NCH * 128 + KP * SS * 8;
-  constexpr int GU = STEP > 0 ? S * STEP : 2, NSTU = IWB2_U_NST;
-  constexpr int STAGE_U = (GU * NCH * 128 + GU * SS * 8 + 127) & ~127;
+  constexpr int TP = iwb2_tile_pitch(KP * NCH + 3);             // general path: floats per tile row (+3: start rounded down)
+  static_assert((KP * NCH) % 4 == 0, "general stages advance by whole 16-byte chunks");
+  constexpr int STAGE = (32 * TP * 4 + KP * SS * 8 + 127) & ~127;
+  constexpr int GU = STEP > 0 ? S * STEP : 4, NSTU = IWB2_U_NST;
+  constexpr int TPU = iwb2_tile_pitch(GU * NCH);                // uniform path
+  constexpr int STAGE_U = (32 * TPU * 4 + GU * SS * 8 + 127) & ~127;
+  static_assert(STEP == 0 || (GU * NCH) % 4 == 0, "a uniform stage must end on a 16-byte chunk");
   constexpr int RING = NST * STAGE > NSTU * STAGE_U ? NST * STAGE : NSTU * STAGE_U;
   constexpr int WARP_BYTES = (RING + 32 * IWB2_OST_PITCH + 8 * 8 + 127) & ~127;
-  constexpr int FU = NCH == 3 ? 40 : 128;                       // pixels per flush (FU * NCH bytes <= 128, multiple of 4)
+  constexpr int FU = ((IWB2_OST_PITCH - 4) / NCH) & ~3;         // pixels per flush (multiple of 4; FU * NCH bytes fit a staging row)
   static_assert(KP >= 2 && NST >= 3 && GU >= 2 && NSTU >= 2, "pipeline depth");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -444,7 +454,6 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS) iwb_h2(const H2Params p) {
   const bool active = jb < p.row_hi;
   const int y = jb + lane;
   const unsigned ring0 = s2_addr(wbase);
-  const float *gbase = p.inter + (size_t)grp * p.ncols_pad * 32;
 
   int b0 = 0, nb = 0, xb = xo0, nout = 0, nstg = 0;             // general-path geometry
   int og0 = 0, ncyc = 0, B0 = 0;                                // uniform-path geometry (see the vertical kernel)
@@ -459,23 +468,26 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS) iwb_h2(const H2Params p) {
     nout = xo1 - xb;
     nstg = (nb + KP - 1) / KP;
   }
-  // stage n = KP (GU) pixel columns of this row group -- one contiguous block of the blocked transposed
-  // intermediate, which is padded on both sides so that a stage may start before column 0 or end after the last
-  // one (those columns meet zero weights) -- + the schedule rows of weights
+  // stage n = KP (GU) pixel columns x this warp's 32 rows of the row-major intermediate as one 2-D TMA tile
+  // (columns / rows outside the tensor are zero-filled: they meet zero weights or rows that are not stored) + the
+  // schedule rows of weights
+  // (pixel x, channel c is float x*NCH + c + p.sh of a row.  TMA tiles must start on 16 bytes: the general path
+  // rounds the start down and skips the 0..3 leading floats; uniform stages start aligned by the choice of p.sh.)
+  const int gskip = (b0 * NCH + p.sh) & 3;                      // (KP*NCH is a multiple of 4: the same for every stage)
   auto fill = [&](int n, int slot) {
     if (s2_elect()) {
       const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE;
-      s2_mbar_expect(bar, KP * NCH * 128 + KP * SS * 8);
-      s2_bulk_g2s(dst, gbase + (ptrdiff_t)(b0 + n * KP) * NCH * 32, KP * NCH * 128, bar);
-      s2_bulk_g2s(dst + KP * NCH * 128, p.sc.w + (ptrdiff_t)(b0 + n * KP) * SS, KP * SS * 8, bar);
+      s2_mbar_expect(bar, 32 * TP * 4 + KP * SS * 8);
+      s2_tma_2d(dst, &tmap, (b0 + n * KP) * NCH + p.sh - gskip, grp * 32, bar);
+      s2_bulk_g2s(dst + 32 * TP * 4, p.sc.w + (ptrdiff_t)(b0 + n * KP) * SS, KP * SS * 8, bar);
     }
   };
   auto fill_u = [&](int n, int slot) {
     if (s2_elect()) {
       const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE_U;
-      s2_mbar_expect(bar, GU * NCH * 128 + GU * SS * 8);
-      s2_bulk_g2s(dst, gbase + (ptrdiff_t)(B0 + n * GU) * NCH * 32, GU * NCH * 128, bar);
-      s2_bulk_g2s(dst + GU * NCH * 128, p.sc.w + (ptrdiff_t)(B0 + n * GU) * SS, GU * SS * 8, bar);
+      s2_mbar_expect(bar, 32 * TPU * 4 + GU * SS * 8);
+      s2_tma_2d(dst, &tmap_u, (B0 + n * GU) * NCH + p.sh, grp * 32, bar);
+      s2_bulk_g2s(dst + 32 * TPU * 4, p.sc.w + (ptrdiff_t)(B0 + n * GU) * SS, GU * SS * 8, bar);
     }
   };
   // prologue: start this warp's pipeline and the (asynchronous) copy of the decision tables, then the small loops
@@ -531,8 +543,8 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS) iwb_h2(const H2Params p) {
   }
   const float *ord_t = ord_s + (y & 7) * 8;                     // this row's eight ordered-dither thresholds
 
-  // one input pixel column: `nxt` is the shared-memory address of the next column's first channel for this lane
-  auto taps = [&](double (&vc)[NCH], unsigned nxt, unsigned wrow) {
+  // one input pixel column; nf[] = the next column's samples (already on their way from shared memory)
+  auto taps = [&](double (&vc)[NCH], const float (&nf)[NCH], unsigned wrow) {
     double2 w[SS / 2];
 #pragma unroll
     for (int s2 = 0; s2 < SS / 2; s2++) w[s2] = s2_ldsw(wrow + 16 * s2);
@@ -547,7 +559,7 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS) iwb_h2(const H2Params p) {
           acc[s][c] = __dadd_rn(acc[s][c], __dmul_rn(vc[c], (s & 1) ? w[s >> 1].y : w[s >> 1].x));
         }
       }
-      vc[c] = (double)s2_ldsf(nxt + 128 * c);                   // next column, in place
+      vc[c] = (double)nf[c];                                    // next column, in place
     }
   };
 
@@ -590,19 +602,33 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS) iwb_h2(const H2Params p) {
     int slot = 0;
     unsigned par = 0;
     s2_mbar_wait(bar0, 0);
+    // This lane's row of the tile is read 16 bytes at a time (conflict-free, see iwb2_tile_pitch); `ch` is the
+    // chunk holding the next sample to hand out.  Every index below is a compile-time constant after unrolling.
+    const unsigned rowoff = lane * (TPU * 4);
+    float4 ch;
+    auto lds128 = [](unsigned a) { float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v; };
+    auto elem = [](const float4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); };
+    ch = lds128(ring0 + rowoff);
     double vc[NCH];
 #pragma unroll
-    for (int c = 0; c < NCH; c++) vc[c] = (double)s2_ldsf(ring0 + lane * 4 + 128 * c);   // column 0
+    for (int c = 0; c < NCH; c++) vc[c] = (double)elem(ch, c);  // column 0 (NCH <= 4: inside the first chunk)
     for (int cyc = 0; cyc < ncyc; cyc++) {
       const int nslot = slot + 1 == NSTU ? 0 : slot + 1;
       const unsigned npar = nslot == 0 ? par ^ 1 : par;
-      const unsigned sb = ring0 + slot * STAGE_U + lane * 4, sbn = ring0 + nslot * STAGE_U + lane * 4;
-      const unsigned wb = ring0 + slot * STAGE_U + GU * NCH * 128;
+      const unsigned sb = ring0 + slot * STAGE_U + rowoff, sbn = ring0 + nslot * STAGE_U + rowoff;
+      const unsigned wb = ring0 + slot * STAGE_U + 32 * TPU * 4;
       const int og = og0 + cyc * S;
 #pragma unroll
       for (int r = 0; r < GU; r++) {
         if (r == GU - 1) s2_mbar_wait(bar0 + 8 * nslot, npar);  // the last column prefetches from the next stage
-        taps(vc, r + 1 < GU ? sb + (r + 1) * NCH * 128 : sbn, wb + r * SS * 8);
+        float nf[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+          const int f = (r + 1 < GU ? (r + 1) * NCH : 0) + c;   // flat index of the sample within its stage
+          if (f % 4 == 0) ch = lds128((r + 1 < GU ? sb : sbn) + f * 4);
+          nf[c] = elem(ch, f % 4);
+        }
+        taps(vc, nf, wb + r * SS * 8);
         if ((r + 1) % STEP == 0) finish((r + 1) / STEP - 1, og + (r + 1) / STEP - 1);
       }
       __syncwarp();
@@ -619,9 +645,12 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS) iwb_h2(const H2Params p) {
   int ld_stage = 0, ld_slot = 0, w_slot = 0;
   unsigned parity = 0;
   s2_mbar_wait(bar0, 0);
-  unsigned pin = ring0 + lane * 4;
-  unsigned pin_end = pin + KP * NCH * 128;
-  unsigned pw = ring0 + KP * NCH * 128;
+  // (this path reads its row of the tile 4 bytes at a time, which costs a 4-way bank conflict per load; it serves
+  // the image borders and non-integer scale factors)
+  const unsigned rowoff = lane * (TP * 4) + gskip * 4;
+  unsigned pin = ring0 + rowoff;
+  unsigned pin_end = pin + KP * NCH * 4;
+  unsigned pw = ring0 + 32 * TP * 4;
   unsigned pw_end = pw + KP * SS * 8;
   auto advance_load = [&]() {
     __syncwarp();
@@ -629,23 +658,26 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS) iwb_h2(const H2Params p) {
     ld_stage++;
     if (++ld_slot == NST) { ld_slot = 0; parity ^= 1; }
     if (ld_stage < nstg) s2_mbar_wait(bar0 + 8 * ld_slot, parity);
-    pin = ring0 + ld_slot * STAGE + lane * 4;
-    pin_end = pin + KP * NCH * 128;
+    pin = ring0 + ld_slot * STAGE + rowoff;
+    pin_end = pin + KP * NCH * 4;
   };
   double vc[NCH];
 #pragma unroll
-  for (int c = 0; c < NCH; c++) vc[c] = (double)s2_ldsf(pin + 128 * c);       // pixel column 0
-  pin += NCH * 128;
+  for (int c = 0; c < NCH; c++) vc[c] = (double)s2_ldsf(pin + 4 * c);         // pixel column 0
+  pin += NCH * 4;
   if (pin == pin_end) advance_load();
   int i = 0;                                                    // pixel column being consumed (relative to b0)
   auto col_step = [&]() {
-    taps(vc, pin, pw);
-    pin += NCH * 128;
+    float nf[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) nf[c] = s2_ldsf(pin + 4 * c);
+    taps(vc, nf, pw);
+    pin += NCH * 4;
     if (pin == pin_end) advance_load();
     pw += SS * 8;
     if (pw == pw_end) {
       if (++w_slot == NST) w_slot = 0;
-      pw = ring0 + w_slot * STAGE + KP * NCH * 128;
+      pw = ring0 + w_slot * STAGE + 32 * TP * 4;
       pw_end = pw + KP * SS * 8;
     }
     i++;

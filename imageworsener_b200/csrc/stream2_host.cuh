@@ -6,13 +6,14 @@
 
 #include "stream2_dev.cuh"
 
-// (slots, uniform step) pairs the kernels are instantiated for; a cycle is S*STEP inputs (4..IWB2_MAX_GU)
+// (slots, uniform step) pairs the kernels are instantiated for; a cycle is S*STEP inputs: a multiple of 4 (the
+// horizontal kernel reads 16-byte chunks, and a stage must end on one for 1 and 3 channels alike), 4..IWB2_MAX_GU
 #ifdef IWB_QUICK
 #define IWB2_UNIFORM_PAIRS(X) X(6, 2)
 #define IWB2_GENERAL_S(X) X(6)
 #else
 #define IWB2_UNIFORM_PAIRS(X) \
-  X(2, 2) X(3, 2) X(4, 2) X(5, 2) X(6, 2) X(8, 2) X(2, 3) X(3, 3) X(4, 3) X(5, 3) X(2, 4) X(3, 4) X(4, 4)
+  X(2, 2) X(4, 2) X(6, 2) X(8, 2) X(4, 3) X(2, 4) X(3, 4) X(4, 4) X(4, 1) X(8, 1)
 #define IWB2_GENERAL_S(X) X(2) X(3) X(4) X(5) X(6) X(8)
 #endif
 
@@ -123,19 +124,43 @@ static inline size_t iwb2_v_smem(int S, int step, int nout) {
   const int gu = step > 0 ? S * step : 4;
   const size_t stage_u = ((size_t)gu * 128 + (size_t)gu * SS * 8 + 127) & ~(size_t)127;
   const size_t ring = std::max((size_t)IWB2_V_NST * stage, (size_t)IWB2_U_NST * stage_u);
-  const size_t warp_bytes = (ring + 8 * 4 * 32 * 4 + 8 * 8 + 127) & ~(size_t)127;
+  const size_t warp_bytes = (ring + 8 * 8 + 127) & ~(size_t)127;
   return 256 * 16 * 8 + IWB2_V_WARPS * warp_bytes + (size_t)nout * 4 + 16;
 }
 static inline size_t iwb2_h_smem(int S, int step, int nch, int ntab, int nout) {
   const int SS = (S + 1) & ~1;
-  const size_t stage = (size_t)IWB2_H_KP * nch * 128 + (size_t)IWB2_H_KP * SS * 8;
-  const int gu = step > 0 ? S * step : 2;
-  const size_t stage_u = ((size_t)gu * nch * 128 + (size_t)gu * SS * 8 + 127) & ~(size_t)127;
+  const size_t stage = ((size_t)32 * iwb2_tile_pitch(IWB2_H_KP * nch + 3) * 4 + (size_t)IWB2_H_KP * SS * 8 + 127) & ~(size_t)127;
+  const int gu = step > 0 ? S * step : 4;
+  const size_t stage_u = ((size_t)32 * iwb2_tile_pitch(gu * nch) * 4 + (size_t)gu * SS * 8 + 127) & ~(size_t)127;
   const size_t ring = std::max((size_t)IWB2_H_NST * stage, (size_t)IWB2_U_NST * stage_u);
   const size_t warp_bytes = (ring + 32 * IWB2_OST_PITCH + 8 * 8 + 127) & ~(size_t)127;
   return IWB2_H_WARPS * warp_bytes + (size_t)ntab * IWB2_TAB_BYTES + 64 * 4 + 16 + (size_t)nout * 4 + 16;
 }
 
-bool iwb2_run_h_e1(const H2Job &job, cudaStream_t st);
-bool iwb2_run_h_e3(const H2Job &job, cudaStream_t st);
-bool iwb2_run_h_e4(const H2Job &job, cudaStream_t st);
+// The FP32 intermediate of a launch as a 2-D tensor [rows][ncols] (row pitch in floats), tiles of 32 rows x box_cols.
+static inline bool iwb2_make_inter_map(const H2Params &p, int box_cols, CUtensorMap *tm) {
+  iwb2_encode_fn enc = iwb2_tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)(p.ncols + p.sh), (cuuint64_t)(p.row_hi - p.row_lo)};
+  const cuuint64_t gstride[1] = {(cuuint64_t)p.pitch * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p.inter), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Uniform horizontal stages must start on 16 bytes: with window ends E(o) = u_ref_last + step*(o - u_ref_o) the first
+// input pixel of the cycle that starts at output og is E(og) - step + 1, and all cycles of a launch are S*step pixels
+// apart (a multiple of 4), so one shift per launch aligns them all.
+static inline int iwb2_shift_for(const Part2 &pt, int S, int step, int nch) {
+  if (!step || pt.n_u == 0) return 0;
+  int og0 = pt.u_lo - (S - 1);
+  og0 = (og0 >= 0 ? og0 / S : -((-og0 + S - 1) / S)) * S;
+  const long B0 = (long)pt.u_ref_last + (long)step * (og0 - pt.u_ref_o) - step + 1;
+  const long m = ((B0 * nch) % 4 + 4) % 4;
+  return (int)((4 - m) % 4);
+}
+
+bool iwb2_run_h_e1(const H2Job &job, cudaStream_t st, int *shift_only);
+bool iwb2_run_h_e3(const H2Job &job, cudaStream_t st, int *shift_only);
+bool iwb2_run_h_e4(const H2Job &job, cudaStream_t st, int *shift_only);

@@ -27,7 +27,7 @@ static bool run_v(const V2Job &job, int step_found, cudaStream_t st) {
   const int colblocks = (p.ncols + 128 * IWB2_V_WARPS - 1) / (128 * IWB2_V_WARPS);
   const int slots = iwb2_sm_count() * iwb2_ctas_per_sm(iwb_v2<S, STEP>, threads, iwb2_v_smem(S, STEP, 64 + S));
   int nparts = 0;
-  iwb2_plan_parts(job.last_host, p.sc.n_out, p.row_lo, p.row_hi, p.row_base, 8, S, slots / colblocks, job.strip_override, 32,
+  iwb2_plan_parts(job.last_host, p.sc.n_out, p.row_lo, p.row_hi, p.row_base, 1, S, slots / colblocks, job.strip_override, 16,
                   step_found == STEP ? STEP : 0, &p.part, &nparts);
   const int nout = std::max(p.part.g_len, 8) + S;
   CUtensorMap tm, tmu;
@@ -52,11 +52,16 @@ bool iwb2_run_v(const V2Job &job, cudaStream_t st) {
   return false;
 }
 
-bool iwb2_run_h(const H2Job &job, cudaStream_t st) {
+static bool run_h_any(const H2Job &job, cudaStream_t st, int *shift_only) {
   switch (job.epi) {
-    case 1: return iwb2_run_h_e1(job, st);
-    case 3: return iwb2_run_h_e3(job, st);
-    case 4: return iwb2_run_h_e4(job, st);
+    case 1: return iwb2_run_h_e1(job, st, shift_only);
+    case 3: return iwb2_run_h_e3(job, st, shift_only);
+    case 4: return iwb2_run_h_e4(job, st, shift_only);
   }
   return false;
+}
+bool iwb2_run_h(const H2Job &job, cudaStream_t st) { return run_h_any(job, st, nullptr); }
+int iwb2_h_shift(const H2Job &job) {
+  int sh = 0;
+  return run_h_any(job, 0, &sh) ? sh : 0;
 }
