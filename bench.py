@@ -31,7 +31,19 @@ import numpy as np  # noqa: E402
 from imageworsener_b200 import configs, libimagew as L  # noqa: E402
 
 METRIC = "output Mpix/s, 8K->4K Lanczos3 linear-light RGB8 + ordered dither"
-KERNEL_CLASSES = ["v_pass", "h_pass_epilogue", "prng_fill", "errdiff", "post", "fused_vh_tile"]
+KERNEL_CLASSES = ["v_pass_generic", "h_pass_epilogue", "prng_fill", "errdiff", "post", "v_pass_stream"]
+# measured FP64 issue rate for independent DMUL+DADD pairs (tools/fp64_peak.cu, profiles/r1_fp64_peak.txt)
+FP64_PEAK_LANE_INSTR = 18.4e12
+
+
+def ncu_traffic(kernel_class: str):
+    """DRAM bytes (read + write) per launch of the kernel class from the committed `ncu --set full` capture of
+    this same command (profiles/traffic.json, written by tools/ncu_summary.py); None if not recorded."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(kernel_class)
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def env_int(name, default):
@@ -327,12 +339,20 @@ def main():
     avg_launch_ms = stats[dom]["ms_per_step"] / lp
     achieved = (alg_bytes_step / lp) / (avg_launch_ms * 1e-3) / 1e9   # GB/s, algorithmic bytes of the rows a launch covers
     peak, peak_src = measured_peak_hbm()
+    taps = info.taps_v + info.taps_h
+    step_gbs = alg_bytes_step / (ms_per_step * 1e-3) / 1e9
+    fp64_rate = 2.0 * taps / (ms_per_step * 1e-3)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
                 "algorithmic_bytes_per_step": alg_bytes_step, "launches_per_step": lp,
                 "avg_launch_ms": avg_launch_ms, "kernel_ms_per_step": stats,
-                "fp64_tap_pairs_per_step": info.taps_v + info.taps_h,
-                "note": "FP64 issue (DMUL+DADD per tap, FMA forbidden by bit-exactness) binds before HBM; see DESIGN.md"}
+                "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak},
+                "fp64_tap_pairs_per_step": taps,
+                "fp64": {"achieved_lane_instr_per_s": fp64_rate, "peak_lane_instr_per_s": FP64_PEAK_LANE_INSTR,
+                         "frac": fp64_rate / FP64_PEAK_LANE_INSTR,
+                         "hbm_frac_ceiling": (alg_bytes_step / peak / 1e9) / (2.0 * taps / FP64_PEAK_LANE_INSTR)},
+                "note": "every tap is one DMUL + one DADD (FMA forbidden by bit-exactness): the FP64 pipe binds before "
+                        "HBM, `fp64.hbm_frac_ceiling` is the HBM fraction at 100 % FP64 issue; see DESIGN.md"}
     dll.iwb200_job_destroy(job)
     lib.iw_destroy_context(ctx)
 

@@ -19,6 +19,18 @@ raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_outpu
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
 print('kernel:', vals[hdr.index('Kernel Name')])
+if '--traffic' in sys.argv:      # record DRAM bytes per launch for bench.py's roofline.traffic
+    import json, os
+    kname = vals[hdr.index('Kernel Name')]
+    cls = 'v_pass_stream' if 'iwb_v2' in kname or 'vstream' in kname else ('h_pass_epilogue' if 'iwb_h2' in kname or 'hstream' in kname else kname)
+    def num(m):
+        i = hdr.index(m); v = float(vals[i].replace(',', '')); u = units[i]
+        return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
+    tp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles', 'traffic.json')
+    d = json.load(open(tp)) if os.path.exists(tp) else {}
+    d[cls] = num('dram__bytes_read.sum') + num('dram__bytes_write.sum')
+    json.dump(d, open(tp, 'w'), indent=1)
+    sys.argv.remove('--traffic')
 for w in WANT:
     if w in hdr:
         i = hdr.index(w)
