@@ -370,17 +370,13 @@ __device__ __noinline__ int exact8_v2(const double *thr, int top, double s, int 
   return frac >= th ? q + 1 : q;
 }
 
+// FP32 decision, branch-free: returns the code and whether it is settled (outside the error margin).  The
+// channels of a pixel are evaluated side by side (no branch between them, so their table-lookup chains overlap)
+// and the rare unsettled samples are redone exactly afterwards, behind one warp vote.
 template <int EPI>
-__device__ __forceinline__ int quantise8_v2(const unsigned char *tab, float margin, int top, float t, double s, uint32_t draw) {
+__device__ __forceinline__ int quantise8_try(const unsigned char *tab, float margin, int top, float t, double s, bool *sure, int *qguess) {
   const float4 *e4_s = (const float4 *)tab;
   const uint16_t *hint_s = (const uint16_t *)(tab + IWB2_TAB_HINT);
-  const double *thr_s = (const double *)(tab + IWB2_TAB_THR);
-  if (EPI == 4) {
-    // random dither compares against draw/0xffffffff which can be exactly 0 or 1: keep the reference's exact
-    // end cases (src/imagew-main.c:618-621, :684-685)
-    if (!(s > 0.0)) return 0;
-    if (s > 0.999999999) return top;
-  }
   const float sf = __saturatef((float)s);                       // NaN/negative -> 0, > 1 -> 1
   const int b = (int)(sf * (float)IWB2_NHINT);
   const int q0 = hint_s[b];
@@ -390,10 +386,18 @@ __device__ __forceinline__ int quantise8_v2(const unsigned char *tab, float marg
   const int q = q0 + (up ? 1 : 0);
   const float fr = (sf - lo) * inv;
   const float d = fr - t;
+  int code = q + (d >= 0.0f ? 1 : 0);
   // random thresholds reach 0 and 1: a sample within the margin of a level boundary also goes the exact way
-  const bool sure = EPI == 4 ? (fabsf(d) > margin && fr > margin && fr < 1.0f - margin) : fabsf(d) > margin;
-  if (sure) return q + (d >= 0.0f ? 1 : 0);
-  return exact8_v2<EPI == 1 ? 0 : (EPI == 3 ? 1 : 3)>(thr_s, top, s, q, t, draw);
+  bool ok = EPI == 4 ? (fabsf(d) > margin && fr > margin && fr < 1.0f - margin) : fabsf(d) > margin;
+  if (EPI == 4) {
+    // random dither compares against draw/0xffffffff which can be exactly 0 or 1: keep the reference's exact
+    // end cases (src/imagew-main.c:618-621, :684-685)
+    if (!(s > 0.0)) { code = 0; ok = true; }
+    if (s > 0.999999999) { code = top; ok = true; }
+  }
+  *sure = ok;
+  *qguess = q;
+  return code;
 }
 
 // Write the warp's staged output bytes: `nrows` rows of `nbytes` bytes, coalesced per row (4-byte words when the
@@ -579,19 +583,35 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
     if (xo >= xo0 && xo < xo1) {
       if (xo - staged_from >= FU) flush(xo);
       unsigned char *dstb = ost_t + (xo - staged_from) * NCH;
-      float t = 0.5f;
-      if (EPI == 3) t = ord_t[xo & 7];
+      float t[NCH];
+      uint32_t draw[NCH];
+      int code[NCH], qg[NCH];
+      bool sure[NCH], all_sure = true;
 #pragma unroll
       for (int c = 0; c < NCH; c++) {
-        uint32_t draw = 0;
+        t[c] = EPI == 3 ? ord_t[xo & 7] : 0.5f;
+        draw[c] = 0;
         if (EPI == 4) {
-          draw = iwb_prng_draw_of(rng[c]);
+          draw[c] = iwb_prng_draw_of(rng[c]);
           rng[c] = iwb_prng_step(rng[c]);
-          t = (float)draw * (1.0f / 4294967295.0f);
+          t[c] = (float)draw[c] * (1.0f / 4294967295.0f);
         }
         const int tb = p.same_tables ? 0 : c;
-        dstb[c] = (uint8_t)quantise8_v2<EPI>(tab_s + (size_t)tb * IWB2_TAB_BYTES, p.q[tb].margin, p.q[tb].top, t, acc[k][c], draw);
+        code[c] = quantise8_try<EPI>(tab_s + (size_t)tb * IWB2_TAB_BYTES, p.q[tb].margin, p.q[tb].top, t[c], acc[k][c], &sure[c], &qg[c]);
+        all_sure = all_sure && sure[c];
       }
+      if (__any_sync(0xffffffffu, !all_sure)) {                 // a few 1e-4 of the samples: exact FP64 decision
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+          if (!sure[c]) {
+            const int tb = p.same_tables ? 0 : c;
+            code[c] = exact8_v2<EPI == 1 ? 0 : (EPI == 3 ? 1 : 3)>((const double *)(tab_s + (size_t)tb * IWB2_TAB_BYTES + IWB2_TAB_THR),
+                                                                 p.q[tb].top, acc[k][c], qg[c], t[c], draw[c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NCH; c++) dstb[c] = (uint8_t)code[c];
     }
 #pragma unroll
     for (int c = 0; c < NCH; c++) acc[k][c] = 0.0;
