@@ -212,6 +212,10 @@ struct iwb200_job {
   uint32_t *draws[4] = {nullptr, nullptr, nullptr, nullptr};
   double *errrows[4] = {nullptr, nullptr, nullptr, nullptr};
   int errdiff_next_row = 0;
+  // where the FP32 intermediate of the last chunk lives (iwb200_job_read_intermediate)
+  int last_path = -1, last_c0 = 0, last_c1 = 0, last_sh = 0;
+  size_t last_pitch = 0;
+  const float *last_inter = nullptr;
   // optional per-kernel event timing
   int profiling = 0;
   struct timed { int which; void *a, *b; };
@@ -772,6 +776,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
       if (const char *o2 = iwb_option(ctx, "cuda:strip2")) f->strip2 = std::max(8, atoi(o2) & ~7);
       if (const char *o2 = iwb_option(ctx, "cuda:seg2")) f->seg2 = std::max(4, atoi(o2) & ~3);
       if (const char *o2 = iwb_option(ctx, "cuda:uniform")) f->uniform = atoi(o2) != 0;
+      if (const char *o2 = iwb_option(ctx, "cuda:overlap")) f->overlap = std::max(1, std::min(32, atoi(o2)));
       f->v2 = ok ? 1 : 0;
     }
   }
@@ -791,11 +796,41 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
   // second-generation kernels: TMA needs 16-byte aligned rows
   const uint8_t *src0 = in.pix + (ptrdiff_t)(in.y0 - in.row_origin) * (ptrdiff_t)in.bpr + (size_t)in.x0 * nch;
   if (f->v2 && in.bpr % 16 == 0 && ((uintptr_t)src0 & 15) == 0) {
-    for (int c0 = r0; c0 < r1; c0 += f->chunk_rows) {
-      const int c1 = std::min(r1, c0 + f->chunk_rows);
+    // The two kernels leave different units idle (V: FP64-heavy, H: latency-bound epilogue), so sub-chunks of
+    // output rows are software-pipelined over two streams: H of sub-chunk i (auxiliary stream) runs beside V of
+    // sub-chunk i+1 (caller's stream); the intermediate buffer is used in two halves (ping-pong).
+    int nsub = f->overlap;
+    const int rows_all = r1 - r0;
+    if (nsub < 2 || rows_all < 64 * nsub || job->profiling) nsub = 1;
+    const int half_rows = f->chunk_rows / 2;
+    const size_t pitch = (size_t)f->ncols_pad + 4;
+    cudaStream_t sv = (cudaStream_t)stream, sh = sv;
+    if (nsub > 1) {
+      if (!f->aux_stream) { cudaStream_t t; cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking); f->aux_stream = t; }
+      while ((int)f->ev.size() < 2 * 64 + 1) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); f->ev.push_back(e); }
+      sh = (cudaStream_t)f->aux_stream;
+      cudaEventRecord((cudaEvent_t)f->ev[128], sv);             // everything queued before this call
+      cudaStreamWaitEvent(sh, (cudaEvent_t)f->ev[128], 0);
+    }
+    // sub-chunk boundaries: equal parts (multiples of 8 rows), each at most one buffer half / one chunk
+    std::vector<int> cuts;
+    {
+      const int cap = nsub > 1 ? half_rows : f->chunk_rows;
+      int parts = std::max(nsub, (rows_all + cap - 1) / cap);
+      parts = std::min(parts, 64);
+      int len = ((rows_all + parts - 1) / parts + 7) & ~7;
+      if (len > cap) len = cap & ~7;
+      for (int c = r0; c < r1; c += len) cuts.push_back(c);
+      cuts.push_back(r1);
+      if ((int)cuts.size() - 1 > 64) nsub = 1;                  // (cannot happen for sane sizes; keeps the event pool bounded)
+    }
+    const int nparts = (int)cuts.size() - 1;
+    for (int i = 0; i < nparts; i++) {
+      const int c0 = cuts[i], c1 = cuts[i + 1];
+      float *inter = f->interT + (nsub > 1 ? (size_t)(i & 1) * half_rows * pitch : 0);
       H2Job hj{};
       H2Params &hp = hj.p;
-      hp.inter = f->interT; hp.pitch = f->ncols_pad + 4; hp.ncols = job->in_w * nch; hp.row_lo = c0; hp.row_hi = c1; hp.sc = *f->s2h;
+      hp.inter = inter; hp.pitch = (int)pitch; hp.ncols = job->in_w * nch; hp.row_lo = c0; hp.row_hi = c1; hp.sc = *f->s2h;
       hp.out_w = out.width; hp.out = out; hp.same_tables = f->same_tables; hp.jump = job->d_jump;
       for (int p = 0; p < 4; p++) { hp.ch[p] = job->cout[p < nch ? p : 0]; hp.q[p] = f->q2[p < nch ? p : 0]; }
       hj.S = f->SH; hj.nch = nch; hj.epi = f->epi; hj.last_host = f->hlast.data(); hj.seg_override = f->seg2; hj.allow_uniform = f->uniform;
@@ -805,31 +840,43 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
       V2Params &vp = vj.p;
       vp.src = src0; vp.bpr = in.bpr; vp.ncols = job->in_w * nch; vp.lut = f->lut; vp.sc = *f->s2v;
       vp.tm_row0 = f->vfirst[c0]; vp.tm_rows = f->vlast[c1 - 1] - f->vfirst[c0] + 1;
-      vp.inter = f->interT; vp.pitch = f->ncols_pad + 4; vp.sh = hp.sh; vp.row_base = c0; vp.row_lo = c0; vp.row_hi = c1;
+      vp.inter = inter; vp.pitch = (int)pitch; vp.sh = hp.sh; vp.row_base = c0; vp.row_lo = c0; vp.row_hi = c1;
       vj.S = f->SV; vj.last_host = f->vlast.data(); vj.strip_override = f->strip2; vj.allow_uniform = f->uniform;
+      job->last_path = 2; job->last_c0 = c0; job->last_c1 = c1; job->last_sh = hp.sh; job->last_pitch = pitch; job->last_inter = inter;
+      if (nsub > 1 && i >= 2) cudaStreamWaitEvent(sv, (cudaEvent_t)f->ev[64 + i - 2], 0);   // this half was read by H(i-2)
       {
         prof_scope ps(job, 5, stream);
-        if (!iwb2_run_v(vj, (cudaStream_t)stream)) return fail(job, "fast path: no vertical kernel variant (gen 2)");
+        if (!iwb2_run_v(vj, sv)) return fail(job, "fast path: no vertical kernel variant (gen 2)");
         g_launches++;
       }
+      if (nsub > 1) {
+        cudaEventRecord((cudaEvent_t)f->ev[i], sv);
+        cudaStreamWaitEvent(sh, (cudaEvent_t)f->ev[i], 0);
+      }
       {
-        prof_scope ps(job, 1, stream);
-        if (!iwb2_run_h(hj, (cudaStream_t)stream)) return fail(job, "fast path: no horizontal kernel variant (gen 2)");
+        prof_scope ps(job, 1, (iwb_stream)sh);
+        if (!iwb2_run_h(hj, sh)) return fail(job, "fast path: no horizontal kernel variant (gen 2)");
         g_launches++;
       }
       if (job->negate) {
         PostParams pp;
         pp.out = out; pp.row0 = c0; pp.row1 = c1; pp.negate = 1; pp.alpha_ch = -1; pp.clear_transparent = 0;
         for (int c = 0; c < 4; c++) pp.maxcode[c] = c < job->ctx->out_nch ? job->ctx->out_ci[c].maxcode : 0;
-        prof_scope ps(job, 4, stream);
-        launch<PostBody>(pp, (size_t)(c1 - c0) * out.width, stream);
+        prof_scope ps(job, 4, (iwb_stream)sh);
+        launch<PostBody>(pp, (size_t)(c1 - c0) * out.width, (iwb_stream)sh);
       }
+      if (nsub > 1) cudaEventRecord((cudaEvent_t)f->ev[64 + i], sh);
+    }
+    if (nsub > 1) {                                             // the caller's stream continues after the last H passes
+      cudaStreamWaitEvent(sv, (cudaEvent_t)f->ev[64 + nparts - 1], 0);
+      if (nparts >= 2) cudaStreamWaitEvent(sv, (cudaEvent_t)f->ev[64 + nparts - 2], 0);
     }
     if (cudaGetLastError() != cudaSuccess) return fail(job, "fast path: kernel launch failed (gen 2)");
     return true;
   }
   for (int c0 = r0; c0 < r1; c0 += f->chunk_rows) {
     const int c1 = std::min(r1, c0 + f->chunk_rows);
+    job->last_path = 1; job->last_c0 = c0; job->last_c1 = c1; job->last_pitch = f->pitch_j; job->last_inter = f->interT;
     VStreamParams vp;
     vp.src = in.pix; vp.bpr = in.bpr; vp.row_origin = in.row_origin; vp.y0 = in.y0;
     vp.x0_bytes = (size_t)in.x0 * nch; vp.ncols = job->in_w * nch; vp.lut = f->lut; vp.sc = f->sv;
@@ -871,6 +918,8 @@ static void job_free(iwb200_job *job) {
 #if !defined(IWB_EMU)
   for (int k = 0; k < 3; k++) if (job->streams[k]) cudaStreamDestroy((cudaStream_t)job->streams[k]);
   for (void *e : job->events) cudaEventDestroy((cudaEvent_t)e);
+  for (void *e : job->fused.ev) cudaEventDestroy((cudaEvent_t)e);
+  if (job->fused.aux_stream) cudaStreamDestroy((cudaStream_t)job->fused.aux_stream);
 #endif
   for (void *p : job->allocs) dev_free(p);
   dev_free(job->d_in);
@@ -1275,6 +1324,7 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
   for (int c0 = r0; c0 < r1; c0 += job->chunk_rows) {
     const int c1 = std::min(r1, c0 + job->chunk_rows);
     const size_t rows = c1 - c0;
+    job->last_path = 0; job->last_c0 = c0; job->last_c1 = c1;
     // vertical pass, all channels
     VPassParams vp;
     vp.in = in; vp.cm = job->cm; vp.nch = job->nproc; vp.in_w = job->in_w; vp.row0 = c0; vp.row1 = c1;
@@ -1329,6 +1379,46 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
   if (cudaGetLastError() != cudaSuccess) return fail(job, "kernel launch failed");
 #endif
   return 1;
+}
+
+// Verification hook: the FP32 intermediate (vertical-pass result, reference: src/imagew-main.c:905-912) of processed
+// channel `ch` for the last chunk of output rows this job ran, as a row-major [rows][in_w] plane.
+int iwb200_job_read_intermediate(iwb200_job *job, int ch, float *dst, size_t capacity, int *row0, int *rows, int *width) {
+  if (job && ch < 0) ch = job->nproc - 1;                       // the channel processed last
+  if (!job || job->last_path < 0 || ch < 0 || ch >= job->nproc) return 0;
+  const int nrows = job->last_c1 - job->last_c0, w = job->in_w;
+  if (row0) *row0 = job->last_c0;
+  if (rows) *rows = nrows;
+  if (width) *width = w;
+  if (!dst) return 1;
+  if (capacity < (size_t)nrows * w) return 0;
+#if !defined(IWB_EMU)
+  cudaSetDevice(job->device);
+  cudaDeviceSynchronize();
+#endif
+  if (job->last_path == 0) {
+    return dev_d2h(dst, job->inter[ch], (size_t)nrows * w * sizeof(float), 0, job->err) && dev_sync(0, job->err);
+  }
+#if !defined(IWB_EMU)
+  const int nch = job->fused.nch;
+  if (job->last_path == 2) {
+    std::vector<float> tmp((size_t)nrows * job->last_pitch);
+    if (!dev_d2h(tmp.data(), job->last_inter, tmp.size() * sizeof(float), 0, job->err) || !dev_sync(0, job->err)) return 0;
+    for (int j = 0; j < nrows; j++)
+      for (int x = 0; x < w; x++) dst[(size_t)j * w + x] = tmp[(size_t)j * job->last_pitch + job->last_sh + (size_t)x * nch + ch];
+    return 1;
+  }
+  {
+    const size_t pj = job->last_pitch;                          // generation 1: interT[byte column][row]
+    std::vector<float> tmp((size_t)w * nch * pj);
+    if (!dev_d2h(tmp.data(), job->last_inter, tmp.size() * sizeof(float), 0, job->err) || !dev_sync(0, job->err)) return 0;
+    for (int j = 0; j < nrows; j++)
+      for (int x = 0; x < w; x++) dst[(size_t)j * w + x] = tmp[((size_t)x * nch + ch) * pj + j];
+    return 1;
+  }
+#else
+  return 0;
+#endif
 }
 
 void iwb200_job_set_profiling(iwb200_job *job, int on) { if (job) job->profiling = on; }

@@ -320,6 +320,13 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
 
 const char *iwb200_job_last_error(const iwb200_job *job);
 
+/* Verification hook for the "intermediate samples" parity bar: after a run, copy the FP32 intermediate plane
+ * (the vertical-pass result the reference keeps in `intermediate32`, src/imagew-main.c:905-912, :1383-1446) of
+ * processed channel `ch` (alpha first, as the reference orders channels; -1 = the one processed last) for the LAST chunk of output rows the
+ * job ran, as a row-major [rows][width] array; dst may be NULL to query the extent.  Returns 1 on success. */
+int iwb200_job_read_intermediate(iwb200_job *job, int ch, float *dst, size_t capacity, int *row0, int *rows,
+                                 int *width);
+
 /* Per-kernel device timing.  When enabled, every launch of this job is bracketed by CUDA events on the launching
  * stream; iwb200_job_kernel_stats() synchronises and returns, for kernel class `which` (0 vertical pass,
  * 1 horizontal pass + epilogue, 2 PRNG fill, 3 error diffusion, 4 post, 5 fused tile kernel), the number of

@@ -1,0 +1,96 @@
+"""Intermediate-sample parity (north star: "intermediate linear samples within 1e-12 relative").
+
+The reference keeps the vertical-pass result as FP32 (src/imagew-main.c:905-912) and does not expose it; the
+oracle restatement (oracle/iw_oracle.c, pinned against the reference build and its golden vectors) keeps the plane
+of the last processed channel.  The CUDA library exposes its FP32 intermediate through the verification hook
+iwb200_job_read_intermediate().  Because the arithmetic order is fixed and the result is rounded to float, the two
+must agree BIT FOR BIT, which is what is asserted (0 mismatches; the 1e-12 bar is implied).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from imageworsener_b200 import configs, libimagew as L
+
+RGB, GRAY = L.IW_IMGTYPE_RGB, L.IW_IMGTYPE_GRAY
+CASES = [
+    ("down2_lanczos_rgb", 512, 384, RGB, 8, 256, 192, "-filter lanczos -dither o", {}),
+    ("down2_lanczos_rgb_general", 512, 384, RGB, 8, 256, 192, "-filter lanczos -dither o", {"cuda:uniform": 0}),
+    ("down2_lanczos_rgb_gen1", 512, 384, RGB, 8, 256, 192, "-filter lanczos -dither o", {"cuda:gen": 1}),
+    ("odd_catrom_gray", 500, 333, GRAY, 8, 217, 140, "-filter catrom -dither r", {}),
+    ("up_mitchell_rgb", 200, 150, RGB, 8, 320, 260, "-filter mitchell", {}),
+    ("gray16_generic", 300, 200, GRAY, 16, 150, 100, "-filter catrom -dither r", {}),
+]
+
+
+class Info(C.Structure):
+    _fields_ = [("out_width", C.c_int), ("out_height", C.c_int), ("out_imgtype", C.c_int),
+                ("out_bit_depth", C.c_int), ("out_sampletype", C.c_int), ("out_channels", C.c_int),
+                ("out_bpr", C.c_size_t), ("in_width_phys", C.c_int), ("in_height_phys", C.c_int),
+                ("in_bpr", C.c_size_t), ("bandable", C.c_int), ("uses_fused_kernel", C.c_int),
+                ("taps_v", C.c_double), ("taps_h", C.c_double)]
+
+
+def _job_api(dll):
+    dll.iwb200_job_get_info.argtypes = [C.c_void_p, C.POINTER(Info)]
+    dll.iwb200_job_create.restype = C.c_void_p
+    dll.iwb200_job_create.argtypes = [C.c_void_p, C.c_int]
+    dll.iwb200_job_destroy.argtypes = [C.c_void_p]
+    dll.iwb200_job_run_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+    dll.iwb200_job_last_error.restype = C.c_char_p
+    dll.iwb200_job_last_error.argtypes = [C.c_void_p]
+    dll.iwb200_job_read_intermediate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int),
+                                                 C.POINTER(C.c_int), C.POINTER(C.c_int)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_fp32_intermediate_is_bit_identical_to_oracle(prod, oracle_port, case):
+    name, iw, ih, typ, depth, ow, oh, extra, opts = case
+    cfg = configs.Config(name, iw, ih, typ, depth, ow, oh, f"-width {ow} -height {oh} {extra}")
+    rows = configs.synth_rows(prod, cfg)
+
+    # oracle: last processed channel's plane
+    from oracle_port import OraclePort
+    olib = OraclePort()
+    octx = olib.iw_create_context(None)
+    olib.set_input_from_numpy(octx, rows, cfg.imgtype, cfg.bit_depth, cfg.in_w, cfg.in_h)
+    cfg.apply(olib, octx)
+    assert olib.iw_process_image(octx), olib.errmsg(octx)
+    want = olib.intermediate(octx)
+    _, opx = olib.get_output_numpy(octx)
+
+    # product, through the job layer so the intermediate can be read back before the job is released
+    dll = prod.dll
+    _job_api(dll)
+    ctx = prod.iw_create_context(None)
+    prod.set_input_from_numpy(ctx, rows, cfg.imgtype, cfg.bit_depth, cfg.in_w, cfg.in_h)
+    for k, v in opts.items():
+        prod.iw_set_option(ctx, k.encode(), str(v).encode())
+    cfg.apply(prod, ctx)
+    job = dll.iwb200_job_create(ctx, 0)
+    assert job, prod.errmsg(ctx)
+    nch = L.imgtype_num_channels(cfg.imgtype)
+    info = Info()
+    dll.iwb200_job_get_info(job, C.byref(info))
+    assert (info.out_width, info.out_height) == (ow, oh)
+    out = np.zeros((oh, info.out_bpr), np.uint8)
+    src = np.ascontiguousarray(rows)
+    ok = dll.iwb200_job_run_host(job, src.ctypes.data, src.strides[0], out.ctypes.data, out.strides[0], 0, oh)
+    assert ok, dll.iwb200_job_last_error(job).decode()
+    r0, nr, w = C.c_int(), C.c_int(), C.c_int()
+    last = -1                                                      # the channel processed last, which is the one the oracle keeps
+    assert dll.iwb200_job_read_intermediate(job, last, None, 0, C.byref(r0), C.byref(nr), C.byref(w))
+    assert (r0.value, nr.value, w.value) == (0, oh, iw), "the whole image must be one chunk at this size"
+    got = np.zeros((nr.value, w.value), np.float32)
+    assert dll.iwb200_job_read_intermediate(job, last, got.ctypes.data, got.size, C.byref(r0), C.byref(nr), C.byref(w))
+    dll.iwb200_job_destroy(job)
+    prod.iw_destroy_context(ctx)
+
+    assert np.array_equal(out, opx), "output bytes differ from the oracle"
+    assert want.shape == got.shape
+    bad = np.argwhere(want.view(np.uint32) != got.view(np.uint32))
+    detail = "; ".join(f"(row {j}, col {i}): oracle {want[j, i]!r} cuda {got[j, i]!r}" for j, i in bad[:6])
+    assert len(bad) == 0, f"{len(bad)} of {got.size} FP32 intermediate samples differ: {detail}"
