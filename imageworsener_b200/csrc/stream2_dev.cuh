@@ -96,13 +96,14 @@ __device__ __forceinline__ void s2_decode_part(const Part2 &pt, int id, int lo, 
 // output rows; walks the input rows of the strip once.  Loads run ahead of the arithmetic: while row i is
 // multiplied, the table values of row i+1 and the ring word of row i+2 are already in flight.
 // ---------------------------------------------------------------------------------------------------------
-template <int S, int STEP>
+template <int S, int STEP, int SH>
 __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
     iwb_v2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_u, const V2Params p) {
   constexpr int SS = (S + 1) & ~1;
   constexpr int G = IWB2_V_G, NST = IWB2_V_NST;                 // general path: rows per stage, stages
   constexpr int STAGE = G * 128 + G * SS * 8;                   // bytes: input rows, then weights
   constexpr int GU = STEP > 0 ? S * STEP : 4, NSTU = IWB2_U_NST;   // uniform path: one cycle per stage
+  constexpr int STEPQ = STEP > 0 ? STEP : 1;
   constexpr int STAGE_U = (GU * 128 + GU * SS * 8 + 127) & ~127;
   constexpr int RING = NST * STAGE > NSTU * STAGE_U ? NST * STAGE : NSTU * STAGE_U;
   constexpr int WARP_BYTES = (RING + 8 * 8 + 127) & ~127;       // TMA tiles land on 128-byte boundaries
@@ -215,35 +216,34 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
     }
   };
   // slot k is complete: add its pending products, round to FP32 (reference: src/imagew-main.c:905-912) and store the
-  // warp's 128 columns of this intermediate row as one coalesced 512-byte segment; restart the slot
+  // warp's 128 columns of this intermediate row as one coalesced 512-byte segment; restart the slot.
+  // Column c is stored at float index c + SH: the shift (0..3, chosen per launch, a template parameter here) puts
+  // the horizontal kernel's tiles on 16-byte boundaries, which its TMA loads need; here it only splits the store.
+  float *outp = p.inter + (ptrdiff_t)(o0 - p.row_base) * p.pitch + SH + col0;   // this thread's 4 floats of row o0
+  const ptrdiff_t out_step = p.pitch;
   auto finish = [&](int k, int o) {
 #pragma unroll
     for (int c = 0; c < 4; c++) if (IWB2_DEFER) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
-    if (o >= o0 && o < o1) {
-      // column c is stored at float index c + sh: the shift (0..3, chosen per launch) puts the horizontal kernel's
-      // tiles on 16-byte boundaries, which its TMA loads need; here it only splits the 16-byte store
-      float *dst = p.inter + (size_t)(o - p.row_base) * p.pitch + p.sh + col0;
+    if (o >= o0 && o < o1) {                                    // emitted rows are consecutive: outp walks down the plane
+      const float f0 = (float)acc[k][0], f1 = (float)acc[k][1], f2 = (float)acc[k][2], f3 = (float)acc[k][3];
       if (full) {
-        const float f0 = (float)acc[k][0], f1 = (float)acc[k][1], f2 = (float)acc[k][2], f3 = (float)acc[k][3];
-        if (p.sh == 0) {
-          *reinterpret_cast<float4 *>(dst) = make_float4(f0, f1, f2, f3);
-        } else if (p.sh == 2) {
-          *reinterpret_cast<float2 *>(dst) = make_float2(f0, f1);
-          *reinterpret_cast<float2 *>(dst + 2) = make_float2(f2, f3);
-        } else if (p.sh == 1) {
-          dst[0] = f0;
-          *reinterpret_cast<float2 *>(dst + 1) = make_float2(f1, f2);
-          dst[3] = f3;
-        } else {
-          *reinterpret_cast<float2 *>(dst + 1) = make_float2(f1, f2);   // (sh == 3: dst + 1 is 8-byte aligned)
-          dst[0] = f0;
-          dst[3] = f3;
+        if (SH == 0) {
+          *reinterpret_cast<float4 *>(outp) = make_float4(f0, f1, f2, f3);
+        } else if (SH == 2) {
+          *reinterpret_cast<float2 *>(outp) = make_float2(f0, f1);
+          *reinterpret_cast<float2 *>(outp + 2) = make_float2(f2, f3);
+        } else {                                                // SH odd: outp + 1 is 8-byte aligned
+          outp[0] = f0;
+          *reinterpret_cast<float2 *>(outp + 1) = make_float2(f1, f2);
+          outp[3] = f3;
         }
       } else {
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-          if (col0 + c < p.ncols) dst[c] = (float)acc[k][c];
+        if (col0 + 0 < p.ncols) outp[0] = f0;
+        if (col0 + 1 < p.ncols) outp[1] = f1;
+        if (col0 + 2 < p.ncols) outp[2] = f2;
+        if (col0 + 3 < p.ncols) outp[3] = f3;
       }
+      outp += out_step;
     }
 #pragma unroll
     for (int c = 0; c < 4; c++) acc[k][c] = 0.0;
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
         const unsigned xcur = xn;
         xn = s2_lds32(r + 2 < GU ? sb + (r + 2) * 128 : sbn + (r + 2 - GU) * 128);   // row r+2
         taps(vc, xcur, wb + r * SS * 8);                        // row r (values of row r+1 from xcur)
-        if ((r + 1) % STEP == 0) finish((r + 1) / STEP - 1, og + (r + 1) / STEP - 1);
+        if ((r + 1) % STEPQ == 0) finish((r + 1) / STEPQ - 1, og + (r + 1) / STEPQ - 1);
       }
       __syncwarp();
       if (cyc + NSTU <= ncyc) fill_u(cyc + NSTU, slot);
@@ -374,13 +374,16 @@ __device__ __noinline__ int exact8_v2(const double *thr, int top, double s, int 
 // channels of a pixel are evaluated side by side (no branch between them, so their table-lookup chains overlap)
 // and the rare unsettled samples are redone exactly afterwards, behind one warp vote.
 template <int EPI>
-__device__ __forceinline__ int quantise8_try(const unsigned char *tab, float margin, int top, float t, double s, bool *sure, int *qguess) {
-  const float4 *e4_s = (const float4 *)tab;
-  const uint16_t *hint_s = (const uint16_t *)(tab + IWB2_TAB_HINT);
+__device__ __forceinline__ int quantise8_try(unsigned tab, float margin, int top, float t, double s, bool *sure, int *qguess) {
+  // (tab = 32-bit shared-memory address of the channel's table blob: explicit ld.shared keeps the address
+  // arithmetic in 32 bits and avoids generic-pointer conversions in the hot path)
   const float sf = __saturatef((float)s);                       // NaN/negative -> 0, > 1 -> 1
   const int b = (int)(sf * (float)IWB2_NHINT);
-  const int q0 = hint_s[b];
-  const float4 e = e4_s[q0];
+  unsigned q0u;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(q0u) : "r"(tab + IWB2_TAB_HINT + 2 * b));
+  const int q0 = (int)q0u;
+  float4 e;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(e.x), "=f"(e.y), "=f"(e.z), "=f"(e.w) : "r"(tab + 16 * q0));
   const bool up = sf >= e.z;
   const float lo = up ? e.z : e.x, inv = up ? e.w : e.y;
   const int q = q0 + (up ? 1 : 0);
@@ -430,6 +433,7 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
   static_assert((KP * NCH) % 4 == 0, "general stages advance by whole 16-byte chunks");
   constexpr int STAGE = (32 * TP * 4 + KP * SS * 8 + 127) & ~127;
   constexpr int GU = STEP > 0 ? S * STEP : 4, NSTU = IWB2_U_NST;
+  constexpr int STEPQ = STEP > 0 ? STEP : 1;
   constexpr int TPU = iwb2_tile_pitch(GU * NCH);                // uniform path
   constexpr int STAGE_U = (32 * TPU * 4 + GU * SS * 8 + 127) & ~127;
   static_assert(STEP == 0 || (GU * NCH) % 4 == 0, "a uniform stage must end on a 16-byte chunk");
@@ -545,7 +549,17 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
       rng[c] = t;
     }
   }
-  const float *ord_t = ord_s + (y & 7) * 8;                     // this row's eight ordered-dither thresholds
+  const unsigned ord_a = s2_addr(ord_s) + (y & 7) * 32;         // this row's eight ordered-dither thresholds
+  unsigned tab_c[NCH];                                          // per channel: table blob address, margin, top level
+  float qmargin[NCH];
+  int qtop[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    const int tb = p.same_tables ? 0 : c;
+    tab_c[c] = s2_addr(tab_s) + tb * IWB2_TAB_BYTES;
+    qmargin[c] = p.q[tb].margin;
+    qtop[c] = p.q[tb].top;
+  }
 
   // one input pixel column; nf[] = the next column's samples (already on their way from shared memory)
   auto taps = [&](double (&vc)[NCH], const float (&nf)[NCH], unsigned wrow) {
@@ -569,7 +583,7 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
 
   // output staging: the warp's 32 rows x up to FU pixels, flushed as 4-byte words (coalesced per row)
   int staged_from = xo0;
-  unsigned char *ost_t = ost + lane * IWB2_OST_PITCH;
+  const unsigned ost_a = s2_addr(ost) + lane * IWB2_OST_PITCH;
   const bool walign = (((uintptr_t)p.out.pix | p.out.bpr) & 3) == 0;
   auto flush = [&](int upto) {
     h2_flush(ost, p.out.pix + (size_t)(jb - p.out.row_origin) * p.out.bpr + (size_t)staged_from * NCH, p.out.bpr,
@@ -582,22 +596,21 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
     for (int c = 0; c < NCH; c++) if (IWB2_DEFER) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
     if (xo >= xo0 && xo < xo1) {
       if (xo - staged_from >= FU) flush(xo);
-      unsigned char *dstb = ost_t + (xo - staged_from) * NCH;
+      const unsigned dstb = ost_a + (xo - staged_from) * NCH;
       float t[NCH];
       uint32_t draw[NCH];
       int code[NCH], qg[NCH];
       bool sure[NCH], all_sure = true;
 #pragma unroll
       for (int c = 0; c < NCH; c++) {
-        t[c] = EPI == 3 ? ord_t[xo & 7] : 0.5f;
+        t[c] = EPI == 3 ? s2_ldsf(ord_a + 4 * (xo & 7)) : 0.5f;
         draw[c] = 0;
         if (EPI == 4) {
           draw[c] = iwb_prng_draw_of(rng[c]);
           rng[c] = iwb_prng_step(rng[c]);
           t[c] = (float)draw[c] * (1.0f / 4294967295.0f);
         }
-        const int tb = p.same_tables ? 0 : c;
-        code[c] = quantise8_try<EPI>(tab_s + (size_t)tb * IWB2_TAB_BYTES, p.q[tb].margin, p.q[tb].top, t[c], acc[k][c], &sure[c], &qg[c]);
+        code[c] = quantise8_try<EPI>(tab_c[c], qmargin[c], qtop[c], t[c], acc[k][c], &sure[c], &qg[c]);
         all_sure = all_sure && sure[c];
       }
       if (__any_sync(0xffffffffu, !all_sure)) {                 // a few 1e-4 of the samples: exact FP64 decision
@@ -611,7 +624,7 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
         }
       }
 #pragma unroll
-      for (int c = 0; c < NCH; c++) dstb[c] = (uint8_t)code[c];
+      for (int c = 0; c < NCH; c++) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dstb + c), "r"(code[c]) : "memory");
     }
 #pragma unroll
     for (int c = 0; c < NCH; c++) acc[k][c] = 0.0;
@@ -649,7 +662,7 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
           nf[c] = elem(ch, f % 4);
         }
         taps(vc, nf, wb + r * SS * 8);
-        if ((r + 1) % STEP == 0) finish((r + 1) / STEP - 1, og + (r + 1) / STEP - 1);
+        if ((r + 1) % STEPQ == 0) finish((r + 1) / STEPQ - 1, og + (r + 1) / STEPQ - 1);
       }
       __syncwarp();
       if (cyc + NSTU <= ncyc) fill_u(cyc + NSTU, slot);

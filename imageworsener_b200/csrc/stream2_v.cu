@@ -20,12 +20,12 @@ static bool make_input_map(const V2Params &p, int box_rows, CUtensorMap *tm) {
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int S, int STEP>
-static bool run_v(const V2Job &job, int step_found, cudaStream_t st) {
+template <int S, int STEP, int SH>
+static bool run_v_sh(const V2Job &job, int step_found, cudaStream_t st) {
   V2Params p = job.p;
   const int threads = 32 * IWB2_V_WARPS;
   const int colblocks = (p.ncols + 128 * IWB2_V_WARPS - 1) / (128 * IWB2_V_WARPS);
-  const int slots = iwb2_sm_count() * iwb2_ctas_per_sm(iwb_v2<S, STEP>, threads, iwb2_v_smem(S, STEP, 64 + S));
+  const int slots = iwb2_sm_count() * iwb2_ctas_per_sm(iwb_v2<S, STEP, SH>, threads, iwb2_v_smem(S, STEP, 64 + S));
   int nparts = 0;
   iwb2_plan_parts(job.last_host, p.sc.n_out, p.row_lo, p.row_hi, p.row_base, 1, S, slots / colblocks, job.strip_override, 16,
                   step_found == STEP ? STEP : 0, &p.part, &nparts);
@@ -33,8 +33,17 @@ static bool run_v(const V2Job &job, int step_found, cudaStream_t st) {
   CUtensorMap tm, tmu;
   if (!make_input_map(p, IWB2_V_G, &tm)) return false;
   if (!make_input_map(p, STEP > 0 ? S * STEP : IWB2_V_G, &tmu)) return false;
-  iwb_v2<S, STEP><<<dim3((unsigned)colblocks, (unsigned)nparts), threads, iwb2_v_smem(S, STEP, nout), st>>>(tm, tmu, p);
+  iwb_v2<S, STEP, SH><<<dim3((unsigned)colblocks, (unsigned)nparts), threads, iwb2_v_smem(S, STEP, nout), st>>>(tm, tmu, p);
   return true;
+}
+template <int S, int STEP>
+static bool run_v(const V2Job &job, int step_found, cudaStream_t st) {
+  switch (job.p.sh & 3) {                                       // the column shift is a compile-time constant of the kernel
+    case 0: return run_v_sh<S, STEP, 0>(job, step_found, st);
+    case 1: return run_v_sh<S, STEP, 1>(job, step_found, st);
+    case 2: return run_v_sh<S, STEP, 2>(job, step_found, st);
+  }
+  return run_v_sh<S, STEP, 3>(job, step_found, st);
 }
 
 bool iwb2_run_v(const V2Job &job, cudaStream_t st) {
