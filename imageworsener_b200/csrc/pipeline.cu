@@ -548,7 +548,9 @@ bool upload_sched2(iwb200_job *job, const HostSched &hs, int n_in, int n_out, Sc
 }
 
 // FP32 decision tables of one channel (threshold-table mode) for quantise8_v2; false = shape not supported.
-bool build_quant2(iwb200_job *job, const std::vector<double> &thr, Quant2 *q) {
+// (nearest = true: the levels are the cells between the nearest-colour midpoints, reference: src/imagew-main.c:638-666;
+// the top cell then ends inside [0, 1] and there is no dither fraction, only "is the sample safely inside its cell")
+bool build_quant2(iwb200_job *job, const std::vector<double> &thr, bool nearest, Quant2 *q) {
   const int n = (int)thr.size();
   if (n < 2 || n > 256) return false;
   const int top = n - 1;
@@ -559,7 +561,7 @@ bool build_quant2(iwb200_job *job, const std::vector<double> &thr, Quant2 *q) {
     lof[k] = (float)lo;
     if (k < top && hi > lo) worst = std::max(worst, hi / (hi - lo));
   }
-  if (lof[0] != 0.0f || lof[top] != 1.0f) return false;         // levels must span exactly [0, 1]
+  if (lof[0] != 0.0f || (!nearest && lof[top] != 1.0f)) return false;   // levels must span exactly [0, 1]
   lof[n] = 3.0f; lof[n + 1] = 3.0f;
   for (int k = 0; k < n; k++) {
     const float hif = k < top ? lof[k + 1] : 2.0f;
@@ -770,8 +772,14 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
       bool ok = upload_sched2(job, hv, job->in_h, job->out.height, f->s2v) && upload_sched2(job, hh, job->in_w, job->out.width, f->s2h);
       f->same_tables = 1;
       for (int p = 0; p < nch && ok; p++) {
-        ok = build_quant2(job, job->thr_host[p], &f->q2[p]);
-        if (p && job->thr_host[p] != job->thr_host[0]) f->same_tables = 0;
+        if (f->epi == 2) {                                       // cells between the nearest-colour midpoints (one table for all)
+          std::vector<double> cells(1, 0.0);
+          cells.insert(cells.end(), job->nc_host.begin(), job->nc_host.end());
+          ok = build_quant2(job, cells, true, &f->q2[p]);
+        } else {
+          ok = build_quant2(job, job->thr_host[p], false, &f->q2[p]);
+          if (p && job->thr_host[p] != job->thr_host[0]) f->same_tables = 0;
+        }
       }
       if (const char *o2 = iwb_option(ctx, "cuda:strip2")) f->strip2 = std::max(8, atoi(o2) & ~7);
       if (const char *o2 = iwb_option(ctx, "cuda:seg2")) f->seg2 = std::max(4, atoi(o2) & ~3);

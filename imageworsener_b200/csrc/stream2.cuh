@@ -58,6 +58,11 @@
 #define IWB2_WPAD 64             // schedule rows of zero weights before row 0 and after the last row
 #define IWB2_MAX_GU 16           // longest uniform cycle (inputs) the kernels are built for
 
+// pipeline geometry of the general path as a function of the kernel's uniform step (0 = general-only kernel)
+__host__ __device__ constexpr int iwb2_v_g(int step) { return step > 0 ? IWB2_V_G : 2 * IWB2_V_G; }
+__host__ __device__ constexpr int iwb2_h_kp(int step) { return step > 0 ? IWB2_H_KP : 2 * IWB2_H_KP; }
+__host__ __device__ constexpr int iwb2_h_nst(int step) { return step > 0 ? IWB2_H_NST : IWB2_H_NST + 1; }
+
 struct Sched2 {                  // device pointers
   const double *w;               // row r at w + r*SS, r in [-IWB2_WPAD, n_in + IWB2_WPAD); SS = S rounded up to even
   const int *first, *last;       // [n_out] window of each output

@@ -100,7 +100,9 @@ template <int S, int STEP, int SH>
 __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
     iwb_v2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_u, const V2Params p) {
   constexpr int SS = (S + 1) & ~1;
-  constexpr int G = IWB2_V_G, NST = IWB2_V_NST;                 // general path: rows per stage, stages
+  // general path: rows per stage, stages.  A general-only kernel (non-integer factors: the whole image takes this
+  // path) gets a deeper pipeline than the general parts of a uniform launch (a few border rows).
+  constexpr int G = iwb2_v_g(STEP), NST = IWB2_V_NST;
   constexpr int STAGE = G * 128 + G * SS * 8;                   // bytes: input rows, then weights
   constexpr int GU = STEP > 0 ? S * STEP : 4, NSTU = IWB2_U_NST;   // uniform path: one cycle per stage
   constexpr int STEPQ = STEP > 0 ? STEP : 1;
@@ -343,7 +345,8 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
 
 // ---------------------------------------------------------------------------------------------------------
 // horizontal kernel + 8-bit epilogue.  Warp = 32 rows (one row group) x one segment of output pixels.
-// EPI: 1 = no dither, 3 = ordered, 4 = random (all channels threshold-table mode, same dither).
+// EPI: 1 = no dither, 3 = ordered, 4 = random (all channels threshold-table mode, same dither); 2 = nearest-colour
+// midpoint table (the reference's fast path for undithered 8-bit output).
 // ---------------------------------------------------------------------------------------------------------
 // ordered-dither matrices (reference: src/imagew-main.c:460-480), entry k means threshold (k + 0.5) / 64
 __constant__ unsigned char iwb2_ord[128] = {
@@ -363,6 +366,7 @@ __device__ __noinline__ int exact8_v2(const double *thr, int top, double s, int 
   while (q < top && thr[q + 1] <= s) q++;
   while (q > 0 && thr[q] > s) q--;
   if (q >= top) return top;
+  if (FAM == 4) return q;                                       // nearest colour: the cell index is the code
   const double d_floor = __dsub_rn(s, thr[q]), d_ceil = __dsub_rn(thr[q + 1], s);
   if (FAM == 0) return d_ceil <= d_floor ? q + 1 : q;
   const double frac = __ddiv_rn(d_floor, __dadd_rn(d_floor, d_ceil));
@@ -392,6 +396,10 @@ __device__ __forceinline__ int quantise8_try(unsigned tab, float margin, int top
   int code = q + (d >= 0.0f ? 1 : 0);
   // random thresholds reach 0 and 1: a sample within the margin of a level boundary also goes the exact way
   bool ok = EPI == 4 ? (fabsf(d) > margin && fr > margin && fr < 1.0f - margin) : fabsf(d) > margin;
+  if (EPI == 2) {                                               // nearest colour: the cell is the code, if safely inside it
+    code = q;
+    ok = fr > margin && fr < 1.0f - margin;
+  }
   if (EPI == 4) {
     // random dither compares against draw/0xffffffff which can be exactly 0 or 1: keep the reference's exact
     // end cases (src/imagew-main.c:618-621, :684-685)
@@ -428,7 +436,7 @@ template <int S, int STEP, int NCH, int EPI>
 __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
     iwb_h2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_u, const H2Params p) {
   constexpr int SS = (S + 1) & ~1;
-  constexpr int KP = IWB2_H_KP, NST = IWB2_H_NST;
+  constexpr int KP = iwb2_h_kp(STEP), NST = iwb2_h_nst(STEP);   // (deeper for a general-only kernel, see iwb_v2)
   constexpr int TP = iwb2_tile_pitch(KP * NCH + 3);             // general path: floats per tile row (+3: start rounded down)
   static_assert((KP * NCH) % 4 == 0, "general stages advance by whole 16-byte chunks");
   constexpr int STAGE = (32 * TP * 4 + KP * SS * 8 + 127) & ~127;
@@ -618,7 +626,7 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
         for (int c = 0; c < NCH; c++) {
           if (!sure[c]) {
             const int tb = p.same_tables ? 0 : c;
-            code[c] = exact8_v2<EPI == 1 ? 0 : (EPI == 3 ? 1 : 3)>((const double *)(tab_s + (size_t)tb * IWB2_TAB_BYTES + IWB2_TAB_THR),
+            code[c] = exact8_v2<EPI == 1 ? 0 : (EPI == 2 ? 4 : (EPI == 3 ? 1 : 3))>((const double *)(tab_s + (size_t)tb * IWB2_TAB_BYTES + IWB2_TAB_THR),
                                                                  p.q[tb].top, acc[k][c], qg[c], t[c], draw[c]);
           }
         }

@@ -95,6 +95,11 @@ static inline int iwb2_plan_parts(const int *last, int n_out, int lo, int hi, in
     if (u_hi - u_lo < std::max(4 * align, 4 * S)) { step = 0; u_lo = u_hi = lo; }
   }
   want = std::max(1, want);
+  // Every part re-reads the inputs of about S outputs in front of it (the windows still open at its start).  When
+  // the launch fills the GPU that halo is pure overhead and parts are as long as one wave allows; a small image
+  // cannot fill the GPU anyway, and then shorter parts (down to 2*S outputs) shorten the critical path instead.
+  (void)g_min;
+  g_min = std::max(align, ((2 * S + align - 1) / align) * align);
   if (!step) { pt->u_ref_o = 0; pt->u_ref_last = 0; }
   if (step) {
     // what is left outside the uniform range: parts of at least g_min outputs, at most about a tenth of the wave
@@ -103,7 +108,7 @@ static inline int iwb2_plan_parts(const int *last, int n_out, int lo, int hi, in
     pt->g_len = std::max(std::max(g_min, align), ((glen + align - 1) / align) * align);
     const int n_g = (u_lo - lo + pt->g_len - 1) / pt->g_len + (hi - u_hi + pt->g_len - 1) / pt->g_len;
     const int n_u_want = std::max(1, want - n_g);
-    int len = len_override > 0 ? len_override : (u_hi - u_lo + n_u_want - 1) / n_u_want;
+    int len = len_override > 0 ? len_override : std::max(g_min, (u_hi - u_lo + n_u_want - 1) / n_u_want);
     len = std::max(align, ((len + align - 1) / align) * align);
     pt->u_lo = u_lo; pt->u_hi = u_hi; pt->u_len = len;
     pt->n_u = (u_hi - u_lo + len - 1) / len;
@@ -120,7 +125,7 @@ static inline int iwb2_plan_parts(const int *last, int n_out, int lo, int hi, in
 
 static inline size_t iwb2_v_smem(int S, int step, int nout) {
   const int SS = (S + 1) & ~1;
-  const size_t stage = (size_t)IWB2_V_G * 128 + (size_t)IWB2_V_G * SS * 8;
+  const size_t stage = (size_t)iwb2_v_g(step) * 128 + (size_t)iwb2_v_g(step) * SS * 8;
   const int gu = step > 0 ? S * step : 4;
   const size_t stage_u = ((size_t)gu * 128 + (size_t)gu * SS * 8 + 127) & ~(size_t)127;
   const size_t ring = std::max((size_t)IWB2_V_NST * stage, (size_t)IWB2_U_NST * stage_u);
@@ -129,10 +134,10 @@ static inline size_t iwb2_v_smem(int S, int step, int nout) {
 }
 static inline size_t iwb2_h_smem(int S, int step, int nch, int ntab, int nout) {
   const int SS = (S + 1) & ~1;
-  const size_t stage = ((size_t)32 * iwb2_tile_pitch(IWB2_H_KP * nch + 3) * 4 + (size_t)IWB2_H_KP * SS * 8 + 127) & ~(size_t)127;
+  const size_t stage = ((size_t)32 * iwb2_tile_pitch(iwb2_h_kp(step) * nch + 3) * 4 + (size_t)iwb2_h_kp(step) * SS * 8 + 127) & ~(size_t)127;
   const int gu = step > 0 ? S * step : 4;
   const size_t stage_u = ((size_t)32 * iwb2_tile_pitch(gu * nch) * 4 + (size_t)gu * SS * 8 + 127) & ~(size_t)127;
-  const size_t ring = std::max((size_t)IWB2_H_NST * stage, (size_t)IWB2_U_NST * stage_u);
+  const size_t ring = std::max((size_t)iwb2_h_nst(step) * stage, (size_t)IWB2_U_NST * stage_u);
   const size_t warp_bytes = (ring + 32 * IWB2_OST_PITCH + 8 * 8 + 127) & ~(size_t)127;
   return IWB2_H_WARPS * warp_bytes + (size_t)ntab * IWB2_TAB_BYTES + 64 * 4 + 16 + (size_t)nout * 4 + 16;
 }
@@ -162,5 +167,6 @@ static inline int iwb2_shift_for(const Part2 &pt, int S, int step, int nch) {
 }
 
 bool iwb2_run_h_e1(const H2Job &job, cudaStream_t st, int *shift_only);
+bool iwb2_run_h_e2(const H2Job &job, cudaStream_t st, int *shift_only);
 bool iwb2_run_h_e3(const H2Job &job, cudaStream_t st, int *shift_only);
 bool iwb2_run_h_e4(const H2Job &job, cudaStream_t st, int *shift_only);

@@ -1,0 +1,103 @@
+"""Host-side planning of the streaming kernels' launches (csrc/stream2_host.cuh: iwb2_plan_parts), without a GPU.
+
+A launch over outputs [lo, hi) is split into `n_u` uniform parts covering [u_lo, u_hi) and general parts covering
+the rest.  Whatever the schedule looks like, the parts must tile [lo, hi) exactly once, respect the alignment, and
+a range may only be called uniform where the window ends really advance by the constant integer step.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from imageworsener_b200 import libimagew as L
+
+
+@pytest.fixture(scope="module")
+def plan():
+    dll = C.CDLL(L.PRODUCT_SO, mode=os.RTLD_LOCAL)
+    fn = dll.iwb200_debug_plan_parts
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+
+    def call(last, lo, hi, base, align, S, want, override, g_min, step_wanted):
+        last = np.ascontiguousarray(last, np.int32)
+        out = np.zeros(9, np.int32)
+        assert fn(last.ctypes.data, len(last), lo, hi, base, align, S, want, override, g_min, step_wanted, out.ctypes.data)
+        return dict(zip("step n_parts n_u u_lo u_hi u_len g_len u_ref_o u_ref_last".split(), map(int, out)))
+    return call
+
+
+def _parts(p, lo, hi):
+    """Decode the parts exactly as the kernels do (stream2_dev.cuh: s2_decode_part)."""
+    out = []
+    for i in range(p["n_parts"]):
+        if i < p["n_u"]:
+            a = p["u_lo"] + i * p["u_len"]
+            out.append((a, min(a + p["u_len"], p["u_hi"]), True))
+            continue
+        g = i - p["n_u"]
+        nh = (p["u_lo"] - lo + p["g_len"] - 1) // p["g_len"]
+        if g < nh:
+            a = lo + g * p["g_len"]
+            out.append((a, min(a + p["g_len"], p["u_lo"]), False))
+        else:
+            a = p["u_hi"] + (g - nh) * p["g_len"]
+            out.append((a, min(a + p["g_len"], hi), False))
+    return out
+
+
+def _sched(n_out, step, jitter_head, jitter_tail, rng):
+    """Window ends: a constant integer step in the middle, irregular (but monotone) near both borders."""
+    last = np.arange(n_out) * step + 5
+    for k in range(jitter_head):
+        last[k] = max(0, last[k] - rng.integers(0, 2))
+    for k in range(n_out - jitter_tail, n_out):
+        last[k] = last[n_out - jitter_tail - 1] + (k - (n_out - jitter_tail - 1)) * max(1, step - 1)
+    return np.maximum.accumulate(last)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_parts_tile_the_launch_and_uniform_ranges_are_uniform(plan, seed):
+    rng = np.random.default_rng(seed)
+    S = int(rng.choice([2, 4, 6, 8]))
+    step = int(rng.choice([1, 2, 3, 4]))
+    n_out = int(rng.integers(40, 3000))
+    last = _sched(n_out, step, int(rng.integers(0, 6)), int(rng.integers(0, 6)), rng)
+    lo = int(rng.integers(0, n_out // 3))
+    hi = int(rng.integers(lo + 8, n_out + 1))
+    align = int(rng.choice([1, 4, 8]))
+    base = lo
+    want = int(rng.integers(1, 60))
+    p = plan(last, lo, hi, base, align, S, want, 0, 16, step)
+    parts = _parts(p, lo, hi)
+    # exact tiling, in order within each class, no empty part
+    cover = np.zeros(n_out, np.int32)
+    for a, b, uni in parts:
+        assert lo <= a < b <= hi
+        cover[a:b] += 1
+        assert (a - base) % align == 0
+    assert np.all(cover[lo:hi] == 1) and cover.sum() == hi - lo
+    if p["step"]:
+        assert p["step"] == step
+        # the progression the kernels assume holds for every output of every uniform part
+        for a, b, uni in parts:
+            if uni:
+                o = np.arange(a, b)
+                assert np.array_equal(last[o], p["u_ref_last"] + p["step"] * (o - p["u_ref_o"]))
+        assert all(b - a >= 1 for a, b, uni in parts if uni)
+    else:
+        assert p["n_u"] == 0
+
+
+def test_small_images_get_short_parts_but_not_shorter_than_their_halo(plan):
+    last = np.arange(144) * 7 + 20                  # 1080 -> 144 rows, far more CTA slots than rows
+    p = plan(last, 0, 144, 0, 1, 5, 37, 0, 16, 0)
+    assert p["n_u"] == 0 and p["g_len"] == 10 and p["n_parts"] == 15      # 2*S outputs per part
+
+
+def test_override_and_no_uniform_request(plan):
+    last = np.arange(1000) * 2 + 6
+    p = plan(last, 0, 1000, 0, 8, 6, 10, 200, 32, 2)
+    assert p["step"] == 2 and p["u_len"] == 200
+    q = plan(last, 0, 1000, 0, 8, 6, 10, 0, 32, 0)
+    assert q["step"] == 0 and q["n_u"] == 0 and q["n_parts"] == (1000 + q["g_len"] - 1) // q["g_len"]
