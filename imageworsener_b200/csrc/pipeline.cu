@@ -1507,7 +1507,20 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
   int copied_to = first - 1;                     // last physical input row already requested
   bool ok = true;
   for (int k = 0; k < nsub && ok; k++) {
-    const int b0 = r0 + (int)(((long long)(r1 - r0) * k) / nsub), b1 = r0 + (int)(((long long)(r1 - r0) * (k + 1)) / nsub);
+    // sub-band boundaries: later sub-bands are shorter, because the call ends with the compute and the copy-out of
+    // the LAST one after the last input byte has arrived (everything else hides behind the input copy)
+    auto cut = [&](int kk) {
+      if (kk <= 0) return r0;
+      if (kk >= nsub) return r1;
+      const double x = (double)kk / nsub;
+      int r = r0 + (int)((double)(r1 - r0) * (1.0 - pow(1.0 - x, 1.6)));
+      return std::min(r1, std::max(r0, (r / 8) * 8));
+    };
+    int b0 = cut(k), b1 = cut(k + 1);
+    if (b1 <= b0 || (nsub > 1 && (r1 - r0) < 64 * nsub)) {       // (degenerate sizes: equal split)
+      b0 = r0 + (int)(((long long)(r1 - r0) * k) / nsub);
+      b1 = r0 + (int)(((long long)(r1 - r0) * (k + 1)) / nsub);
+    }
     int f, l;
     iwb200_job_band_input_rows(job, b0, b1, &f, &l);
     l = std::min(l, last);
