@@ -107,6 +107,8 @@ struct DevChanOut {       // what happens to a resampled intermediate channel
   const double *linval;   // linear value of that code
   double maxcode;
   int color_count;
+  int guess_cs;           // colour space of the table levels (IW_CSTYPE_*), -1: no closed form (plain binary search)
+  float guess_gamma;      // 1/gamma for IW_CSTYPE_GAMMA
   int dfamily, dsubtype;
   uint64_t prng_t1;       // PRNG state after the first step for this channel's seed
   int errdiff;            // this channel goes through the sequential error-diffusion kernel
@@ -297,6 +299,26 @@ IWB_HD Candidates candidates_table(const DevChanOut &o, double s) {
     return c;
   }
   int lo = 0, hi = top;   // invariant: thr[lo] <= s (thr[0] == 0 <= s after clamping)
+  if (o.guess_cs >= 0 && top >= 64) {
+    // Full-depth tables (up to 65 536 levels): start from a single-precision estimate of the level -- the target
+    // curve evaluated in FP32 -- and walk to the exact answer.  The estimate only chooses where the walk starts;
+    // the result is decided by the same exact comparisons against the host-built table as the binary search.
+    const float sf = (float)s;
+    float v;
+    if (o.guess_cs == 0) v = sf <= 0.0031308f ? 12.92f * sf : 1.055f * powf(sf, 1.0f / 2.4f) - 0.055f;
+    else if (o.guess_cs == 3) v = sf < 0.020f ? 4.5f * sf : 1.099f * powf(sf, 0.45f) - 0.099f;
+    else if (o.guess_cs == 2) v = powf(sf, o.guess_gamma);
+    else v = sf;
+    int g = (int)(v * (float)top);
+    g = g < 0 ? 0 : (g > top ? top : g);
+    int steps = 0;
+    while (g < top && o.thr[g + 1] <= s && steps < 8) { g++; steps++; }
+    while (g > 0 && o.thr[g] > s && steps < 16) { g--; steps++; }
+    if (steps < 8 && o.thr[g] <= s && (g == top || o.thr[g + 1] > s)) {
+      lo = g;
+      hi = g;                                   // found: skip the search below
+    }
+  }
   while (hi - lo > 1) {
     int mid = (lo + hi) >> 1;
     if (o.thr[mid] <= s) lo = mid; else hi = mid;

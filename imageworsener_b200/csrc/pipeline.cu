@@ -365,6 +365,9 @@ bool build_output_tables(iwb200_job *job, const iw_context *ctx, const iwb_out_c
     }
   }
   o->ntab = (int)thr.size();
+  // levels of a full-depth table follow the target curve: the device may start its search from an FP32 estimate
+  o->guess_cs = oc.color_count == 0 ? (int)cs.cstype : -1;
+  o->guess_gamma = (cs.cstype == IW_CSTYPE_GAMMA && cs.gamma > 0.0) ? (float)(1.0 / cs.gamma) : 1.0f;
   job->thr_host[job->building_channel] = thr;
   o->thr = job->upload(thr.data(), thr.size());
   o->codeval = job->upload(code.data(), code.size());
