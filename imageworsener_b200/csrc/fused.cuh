@@ -79,7 +79,7 @@ struct FastPlan {
   int nch = 0;
   int SV = 0, SH = 0, NC = 0;
   AxisSched sv{}, sh{};
-  std::vector<int> vfirst, vlast, hlast;   // host copies for band planning / uniform-range detection
+  std::vector<int> vfirst, vlast, hfirst, hlast;   // host copies for band planning / uniform-range detection
   const double *lut = nullptr;
   FastQuant fq[4]{};
   float *interT = nullptr;

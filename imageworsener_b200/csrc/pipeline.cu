@@ -759,6 +759,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
   }
   f->vfirst = hv.first;
   f->vlast = hv.last;
+  f->hfirst = hh.first;
   f->hlast = hh.last;
   f->enabled = 1;
 
@@ -844,7 +845,7 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
       hp.inter = inter; hp.pitch = (int)pitch; hp.ncols = job->in_w * nch; hp.row_lo = c0; hp.row_hi = c1; hp.sc = *f->s2h;
       hp.out_w = out.width; hp.out = out; hp.same_tables = f->same_tables; hp.jump = job->d_jump;
       for (int p = 0; p < 4; p++) { hp.ch[p] = job->cout[p < nch ? p : 0]; hp.q[p] = f->q2[p < nch ? p : 0]; }
-      hj.S = f->SH; hj.nch = nch; hj.epi = f->epi; hj.last_host = f->hlast.data(); hj.seg_override = f->seg2; hj.allow_uniform = f->uniform;
+      hj.S = f->SH; hj.nch = nch; hj.epi = f->epi; hj.first_host = f->hfirst.data(); hj.last_host = f->hlast.data(); hj.seg_override = f->seg2; hj.allow_uniform = f->uniform;
       hp.sh = 0;
       hp.sh = iwb2_h_shift(hj);            // where the horizontal pass wants column 0 (16-byte aligned TMA tiles)
       V2Job vj{};
@@ -852,7 +853,7 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
       vp.src = src0; vp.bpr = in.bpr; vp.ncols = job->in_w * nch; vp.lut = f->lut; vp.sc = *f->s2v;
       vp.tm_row0 = f->vfirst[c0]; vp.tm_rows = f->vlast[c1 - 1] - f->vfirst[c0] + 1;
       vp.inter = inter; vp.pitch = (int)pitch; vp.sh = hp.sh; vp.row_base = c0; vp.row_lo = c0; vp.row_hi = c1;
-      vj.S = f->SV; vj.last_host = f->vlast.data(); vj.strip_override = f->strip2; vj.allow_uniform = f->uniform;
+      vj.S = f->SV; vj.first_host = f->vfirst.data(); vj.last_host = f->vlast.data(); vj.strip_override = f->strip2; vj.allow_uniform = f->uniform;
       job->last_path = 2; job->last_c0 = c0; job->last_c1 = c1; job->last_sh = hp.sh; job->last_pitch = pitch; job->last_inter = inter;
       if (nsub > 1 && i >= 2) cudaStreamWaitEvent(sv, (cudaEvent_t)f->ev[64 + i - 2], 0);   // this half was read by H(i-2)
       {

@@ -125,14 +125,14 @@ struct H2Params {
 struct V2Job {
   V2Params p;                    // everything but `part`
   int S;
-  const int *last_host;          // [n_out] host copy of the schedule's window ends
+  const int *first_host, *last_host;   // [n_out] host copies of the schedule's windows
   int strip_override;            // > 0: rows per uniform strip (tuning)
   int allow_uniform;
 };
 struct H2Job {
   H2Params p;                    // everything but `part`
   int S, nch, epi;
-  const int *last_host;
+  const int *first_host, *last_host;
   int seg_override;
   int allow_uniform;
 };

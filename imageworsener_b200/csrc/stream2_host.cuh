@@ -68,24 +68,35 @@ static int iwb2_ctas_per_sm(K kernel, int threads, size_t smem) {
   return n < 1 ? 1 : n;
 }
 
-// Split outputs [lo, hi) into parts.  `last` = host copy of the schedule's window ends, `base`/`align`: part
-// boundaries must be base + k*align, `want` = how many parts make one full wave.  A uniform range needs a constant
-// integer step between consecutive window ends (the weights themselves come from the schedule table: they are
-// not bitwise periodic in general).  Returns the uniform step (0: none).
-static inline int iwb2_plan_parts(const int *last, int n_out, int lo, int hi, int base, int align, int S, int want, int len_override,
-                                  int g_min, int step_wanted, Part2 *pt, int *nparts) {
+// Split outputs [lo, hi) into parts.  `first` / `last` = host copies of the schedule's windows, `base`/`align`: part
+// boundaries must be base + k*align, `want` = how many parts make one full wave.  An output o may be emitted by the
+// uniform path if (with GU = S*step, the inputs of one cycle)
+//   (1) its window ends exactly `step` inputs after its predecessor's (the progression E(o) the kernels assume);
+//   (2) its slot is free in time: the kernels restart slot o mod S after input E(o) - GU, so the output that used
+//       the slot before (o - S) must end at or before that input, and o's own window must begin after it.
+// Inside a long progression (2) follows from (1); it matters for the first S outputs after a break in the
+// progression (non-integer factors close to an integer) and at the image border.  (The weights themselves come
+// from the schedule table: they are not bitwise periodic in general.)  Returns the uniform step (0: none).
+static inline int iwb2_plan_parts(const int *first, const int *last, int n_out, int lo, int hi, int base, int align, int S, int want,
+                                  int len_override, int g_min, int step_wanted, Part2 *pt, int *nparts) {
   auto up = [&](int v) { return base + ((v - base + align - 1) / align) * align; };
   auto down = [&](int v) { return base + ((v - base) / align) * align; };
   int step = 0, a = lo, b = lo;
   const int mid = lo + (hi - lo) / 2;
-  if (step_wanted > 0 && mid + 1 < n_out && mid >= 0 && last[mid + 1] - last[mid] == step_wanted && iwb2_pair_built(S, step_wanted)) {
+  if (step_wanted > 0 && mid + 1 < n_out && mid >= 1 && last[mid + 1] - last[mid] == step_wanted && iwb2_pair_built(S, step_wanted)) {
     step = step_wanted;
-    a = mid;
-    while (a - 1 >= 0 && last[a] - last[a - 1] == step) a--;
-    b = mid + 1;
-    while (b < n_out && last[b] - last[b - 1] == step) b++;
-    pt->u_ref_o = mid;                                           // any output of the range anchors the progression
-    pt->u_ref_last = last[mid];
+    const int GU = S * step;
+    auto slot_free = [&](int o) { return (o - S < 0 || last[o - S] <= last[o] - GU) && first[o] > last[o] - GU; };
+    if (!slot_free(mid)) {
+      step = 0;
+    } else {
+      a = mid;
+      while (a - 1 >= 0 && last[a] - last[a - 1] == step && slot_free(a - 1)) a--;
+      b = mid + 1;
+      while (b < n_out && last[b] - last[b - 1] == step && slot_free(b)) b++;
+      pt->u_ref_o = mid;                                         // any output of the range anchors the progression
+      pt->u_ref_last = last[mid];
+    }
   }
   int u_lo = lo, u_hi = lo;
   if (step) {

@@ -27,7 +27,7 @@ static bool run_v_sh(const V2Job &job, int step_found, cudaStream_t st) {
   const int colblocks = (p.ncols + 128 * IWB2_V_WARPS - 1) / (128 * IWB2_V_WARPS);
   const int slots = iwb2_sm_count() * iwb2_ctas_per_sm(iwb_v2<S, STEP, SH>, threads, iwb2_v_smem(S, STEP, 64 + S));
   int nparts = 0;
-  iwb2_plan_parts(job.last_host, p.sc.n_out, p.row_lo, p.row_hi, p.row_base, 1, S, slots / colblocks, job.strip_override, 16,
+  iwb2_plan_parts(job.first_host, job.last_host, p.sc.n_out, p.row_lo, p.row_hi, p.row_base, 1, S, slots / colblocks, job.strip_override, 16,
                   step_found == STEP ? STEP : 0, &p.part, &nparts);
   const int nout = std::max(p.part.g_len, 8) + S;
   CUtensorMap tm, tmu;
@@ -78,12 +78,12 @@ int iwb2_h_shift(const H2Job &job) {
 
 // Test hook (tests/test_planner.py): the host-side split of a launch into uniform / general parts, without touching
 // the device.  out[] = {step, n_parts, n_u, u_lo, u_hi, u_len, g_len, u_ref_o, u_ref_last}.
-extern "C" __attribute__((visibility("default"))) int iwb200_debug_plan_parts(const int *last, int n_out, int lo, int hi, int base,
+extern "C" __attribute__((visibility("default"))) int iwb200_debug_plan_parts(const int *first, const int *last, int n_out, int lo, int hi, int base,
                                                                              int align, int S, int want, int len_override, int g_min,
                                                                              int step_wanted, int *out) {
   Part2 pt{};
   int nparts = 0;
-  const int step = iwb2_plan_parts(last, n_out, lo, hi, base, align, S, want, len_override, g_min, step_wanted, &pt, &nparts);
+  const int step = iwb2_plan_parts(first, last, n_out, lo, hi, base, align, S, want, len_override, g_min, step_wanted, &pt, &nparts);
   out[0] = step; out[1] = nparts; out[2] = pt.n_u; out[3] = pt.u_lo; out[4] = pt.u_hi; out[5] = pt.u_len; out[6] = pt.g_len;
   out[7] = pt.u_ref_o; out[8] = pt.u_ref_last;
   return 1;

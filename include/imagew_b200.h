@@ -337,7 +337,7 @@ void iwb200_job_reset_stats(iwb200_job *job);
 
 /* Test hook: the host-side split of one fast-path launch into "uniform" and "general" parts (csrc/stream2_host.cuh);
  * pure host code.  out[9] = {step, n_parts, n_u, u_lo, u_hi, u_len, g_len, u_ref_o, u_ref_last}. */
-int iwb200_debug_plan_parts(const int *last, int n_out, int lo, int hi, int base, int align, int S, int want,
+int iwb200_debug_plan_parts(const int *first, const int *last, int n_out, int lo, int hi, int base, int align, int S, int want,
                             int len_override, int g_min, int step_wanted, int *out);
 
 /* Deterministic synthetic input and output fingerprint used by the benchmarks and the full-size parity tests

@@ -17,12 +17,15 @@ from imageworsener_b200 import libimagew as L
 def plan():
     dll = C.CDLL(L.PRODUCT_SO, mode=os.RTLD_LOCAL)
     fn = dll.iwb200_debug_plan_parts
-    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
 
-    def call(last, lo, hi, base, align, S, want, override, g_min, step_wanted):
+    def call(last, lo, hi, base, align, S, want, override, g_min, step_wanted, first=None):
         last = np.ascontiguousarray(last, np.int32)
+        if first is None:                                          # windows of S*step - 1 inputs: slots are always free in time
+            first = last - (S * max(step_wanted, 1) - 2)
+        first = np.ascontiguousarray(np.maximum(first, 0), np.int32)
         out = np.zeros(9, np.int32)
-        assert fn(last.ctypes.data, len(last), lo, hi, base, align, S, want, override, g_min, step_wanted, out.ctypes.data)
+        assert fn(first.ctypes.data, last.ctypes.data, len(last), lo, hi, base, align, S, want, override, g_min, step_wanted, out.ctypes.data)
         return dict(zip("step n_parts n_u u_lo u_hi u_len g_len u_ref_o u_ref_last".split(), map(int, out)))
     return call
 
@@ -101,3 +104,43 @@ def test_override_and_no_uniform_request(plan):
     assert p["step"] == 2 and p["u_len"] == 200
     q = plan(last, 0, 1000, 0, 8, 6, 10, 0, 32, 0)
     assert q["step"] == 0 and q["n_u"] == 0 and q["n_parts"] == (1000 + q["g_len"] - 1) // q["g_len"]
+
+
+def test_first_outputs_after_a_break_in_the_progression_are_not_uniform(plan):
+    """333 -> 166 pixels with Lanczos3 (factor 2.006): window ends advance by 2 except one 3 in the middle, windows are
+    13 inputs long and 6 are open at once.  The kernels restart a slot S*step = 12 inputs before its output ends, so
+    the outputs right after the break -- whose slots were last used by outputs from BEFORE the break -- must be left
+    to the general path (this was a real bug: their first tap was lost)."""
+    n_in, n_out, S, step = 333, 166, 6, 2
+    o = np.arange(n_out)
+    pos = (o + 0.5) * (n_in / n_out) - 0.5
+    rad = 3.0 * n_in / n_out
+    first = np.maximum(np.ceil(pos - rad), 0).astype(np.int32)
+    last = np.minimum(np.floor(pos + rad), n_in - 1).astype(np.int32)
+    brk = int(np.flatnonzero(np.diff(last)[40:120] != 2)[0]) + 41     # first output after the break
+    p = plan(last, 0, n_out, 0, 4, S, 20, 0, 16, step, first=first)
+    GU = S * step
+    # here every other window is 13 inputs long (> GU), so whatever the planner calls uniform must avoid them all
+    for a, b, uni in _parts(p, 0, n_out):
+        if uni:
+            for q in range(a, b):
+                assert last[q] == p["u_ref_last"] + step * (q - p["u_ref_o"])
+                assert first[q] > last[q] - GU and (q - S < 0 or last[q - S] <= last[q] - GU), (q, brk)
+    assert all(not (uni and a <= brk < b) for a, b, uni in _parts(p, 0, n_out))
+    # A break the other way (one window end advances by 1 instead of 2) with 12-input windows: the S outputs after
+    # it reuse slots whose previous outputs end one input LATER than the progression says -- not uniform either;
+    # everything further away from the break is.
+    brk = 40                                                     # (away from the middle, where the planner anchors)
+    last2 = 2 * o + 6
+    last2[brk:] -= 1
+    first2 = np.maximum(last2 - 11, 0).astype(np.int32)
+    p = plan(last2, 0, n_out, 0, 4, S, 20, 0, 16, step, first=first2)
+    assert p["step"] == 2 and p["n_u"] >= 1
+    parts = _parts(p, 0, n_out)
+    assert all(not (uni and a < brk + S and b > brk) for a, b, uni in parts)
+    assert sum(b - a for a, b, uni in parts if uni) >= 60
+    for a, b, uni in parts:
+        if uni:
+            for q in range(a, b):
+                assert last2[q] == p["u_ref_last"] + step * (q - p["u_ref_o"])
+                assert q - S < 0 or last2[q - S] <= last2[q] - GU

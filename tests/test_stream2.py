@@ -33,6 +33,10 @@ SHAPES = [
     ("tiny", 48, 40, RGB, 24, 20, "-filter lanczos -dither o"),
     ("unaligned_stride", 1022, 300, RGB, 511, 150, "-filter lanczos -dither o"),
     ("box_7p5", 1920, 1080, RGB, 256, 144, "-filter box"),
+    ("down2_lanczos4", 1024, 512, RGB, 512, 256, "-filter lanczos4 -dither o"),        # 8 open windows, step 2
+    ("down4_hermite", 2048, 512, GRAY, 512, 128, "-filter hermite -dither r"),           # 2 open windows, step 4
+    ("down4_quadratic", 2048, 512, RGB, 512, 128, "-filter quadratic"),                  # 3 open windows, step 4
+    ("down2_triangle", 1024, 512, RGB, 512, 256, "-filter triangle -dither halftone"),   # 2 open windows, step 2
 ]
 
 
@@ -74,4 +78,23 @@ def test_fast_path_partition_sizes_do_not_matter(prod, ref, strip, seg):
     rows = configs.synth_rows(prod, cfg)
     _, a = configs.run_host(prod, cfg, rows, options={"cuda:strip2": strip, "cuda:seg2": seg})
     _, b = configs.run_host(ref, cfg, rows)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,typ", [(1001, GRAY), (333, RGB), (1022, RGB)])
+def test_fast_path_padded_rows_with_ragged_last_columns(prod, ref, w, typ):
+    """Rows padded to a multiple of 16 bytes (so the TMA kernels are used) while the number of byte columns is not a
+    multiple of 4 or 128: the last warp's tile is partly outside the tensor and its last thread stores fewer than
+    four columns."""
+    nch = L.imgtype_num_channels(typ)
+    h, ow, oh = 300, w // 2, 150
+    cfg = configs.Config("padded", w, h, typ, 8, ow, oh, f"-width {ow} -height {oh} -filter lanczos -dither o")
+    tight = configs.synth_rows(prod, cfg)
+    bpr = (w * nch + 15) // 16 * 16 + 16
+    rows = np.zeros((h, bpr), np.uint8)
+    rows[:, : w * nch] = tight
+    rows[:, w * nch:] = 0xA5                      # padding bytes must never influence the result
+    ia, a = configs.run_host(prod, cfg, rows)
+    ib, b = configs.run_host(ref, cfg, tight)
     assert np.array_equal(a, b)
