@@ -98,3 +98,35 @@ def test_fast_path_padded_rows_with_ragged_last_columns(prod, ref, w, typ):
     ia, a = configs.run_host(prod, cfg, rows)
     ib, b = configs.run_host(ref, cfg, tight)
     assert np.array_equal(a, b)
+
+
+def _near_integer_case(seed):
+    """8-bit jobs the TMA kernels accept, with scale factors at or next to small integers (where uniform ranges
+    break or windows outgrow a cycle), random filters / dithers / sizes, rows padded to 16 bytes."""
+    rng = np.random.default_rng(seed)
+    typ = RGB if rng.random() < 0.6 else GRAY
+    flt = rng.choice(["lanczos", "lanczos2", "lanczos4", "catrom", "mitchell", "hermite", "triangle", "quadratic", "gaussian",
+                      "bspline", "hann3", "blackman", "box", "mix"])
+    dither = rng.choice(["", "-dither o", "-dither halftone", "-dither r", "-dither r2"])
+    fx, fy = rng.choice([1.5, 2, 3, 4], 2)
+    ow, oh = int(rng.integers(90, 400)), int(rng.integers(40, 160))
+    iw = max(8, int(round(ow * fx)) + int(rng.integers(-3, 4)))
+    ih = max(8, int(round(oh * fy)) + int(rng.integers(-3, 4)))
+    blur = f" -blur {rng.choice([1.0, 1.2, 0.9])}" if rng.random() < 0.25 else ""
+    return configs.Config(f"near{seed}", iw, ih, typ, 8, ow, oh, f"-width {ow} -height {oh} -filter {flt} {dither}{blur}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(80))
+def test_fast_path_near_integer_factors_match_reference(prod, ref, seed):
+    cfg = _near_integer_case(seed)
+    nch = L.imgtype_num_channels(cfg.imgtype)
+    tight = configs.synth_rows(prod, cfg, seed=0x1234 + seed)
+    bpr = (cfg.in_w * nch + 15) // 16 * 16
+    rows = np.full((cfg.in_h, bpr), 0x5A, np.uint8)
+    rows[:, : cfg.in_w * nch] = tight
+    _, b = configs.run_host(ref, cfg, tight)
+    for opts in ({}, {"cuda:uniform": 0}):
+        _, a = configs.run_host(prod, cfg, rows, options=opts)
+        nd = int(np.count_nonzero(a != b))
+        assert nd == 0, f"{cfg.args!r} {cfg.in_w}x{cfg.in_h} {opts}: {nd} differing bytes of {a.size}"
