@@ -45,18 +45,34 @@ def _job_api(dll):
                                                  C.POINTER(C.c_int), C.POINTER(C.c_int)]
 
 
+def _near_cases():
+    from test_stream2 import _near_integer_case
+    out = []
+    for seed in range(100, 124):
+        c = _near_integer_case(seed)
+        out.append((c.name, c.in_w, c.in_h, c.imgtype, 8, c.out_w, c.out_h, c.args.split(f"-height {c.out_h} ", 1)[1], {}, True))
+    return out
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("case", [c + (False,) for c in CASES] + _near_cases(), ids=lambda c: c[0])
 def test_fp32_intermediate_is_bit_identical_to_oracle(prod, oracle_port, case):
-    name, iw, ih, typ, depth, ow, oh, extra, opts = case
+    name, iw, ih, typ, depth, ow, oh, extra, opts, pad = case
     cfg = configs.Config(name, iw, ih, typ, depth, ow, oh, f"-width {ow} -height {oh} {extra}")
     rows = configs.synth_rows(prod, cfg)
+    if pad:                                      # rows padded to 16 bytes so that the TMA kernels take the job
+        nchp = L.imgtype_num_channels(typ)
+        padded = np.full((ih, (iw * nchp + 15) // 16 * 16), 0x33, np.uint8)
+        padded[:, : iw * nchp] = rows
+        tight, rows = rows, padded
+    else:
+        tight = rows
 
     # oracle: last processed channel's plane
     from oracle_port import OraclePort
     olib = OraclePort()
     octx = olib.iw_create_context(None)
-    olib.set_input_from_numpy(octx, rows, cfg.imgtype, cfg.bit_depth, cfg.in_w, cfg.in_h)
+    olib.set_input_from_numpy(octx, tight, cfg.imgtype, cfg.bit_depth, cfg.in_w, cfg.in_h)
     cfg.apply(olib, octx)
     assert olib.iw_process_image(octx), olib.errmsg(octx)
     want = olib.intermediate(octx)
