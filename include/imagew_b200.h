@@ -10,6 +10,12 @@
  *   - the string option "backend" (default and only legal value: "cuda"); there is no CPU path in this
  *     library -- iw_process_image() fails with an error if no CUDA device is usable;
  *   - "cuda:device" (ordinal), "cuda:band" ("index/count": process one output-row band only);
+ *   - tuning / verification options, none of which may change a result byte (tests/test_stream2.py):
+ *     "cuda:gen" (1: first-generation streaming kernels), "cuda:uniform" (0: general path only),
+ *     "cuda:fused" (0: generic per-sample kernels only), "cuda:strip2" / "cuda:seg2" (rows / pixels per CTA part of
+ *     the generation-2 kernels), "cuda:strip" / "cuda:seg" / "cuda:nc" (generation 1), "cuda:chunk_mb" (size of the
+ *     FP32 intermediate), "cuda:pipeline" (sub-bands of the host-buffer pipeline), "cuda:overlap" (two-stream V/H
+ *     overlap, off);
  *   - iwb200_job_*: the plan/launch layer under iw_process_image() for callers that keep images resident
  *     in HBM (benchmarks, multi-GPU band sharding).
  */
