@@ -81,6 +81,7 @@ struct FastPlan {
   AxisSched sv{}, sh{};
   std::vector<int> vfirst, vlast, hfirst, hlast;   // host copies for band planning / uniform-range detection
   const double *lut = nullptr;
+  const double *lut16 = nullptr;                   // generation 2: the same table, each entry repeated 16 times
   FastQuant fq[4]{};
   float *interT = nullptr;
   size_t pitch_j = 0;

@@ -201,6 +201,7 @@ struct iwb200_job {
   double errdiff_m[4][12];
   iwb200_job_info info{};
   int building_channel = 0;
+  std::map<const double *, std::vector<double>> lut_host;   // 8-bit input tables by device address
   std::vector<double> thr_host[4];
   std::vector<double> nc_host;              // nearest-colour midpoints (when that table exists)          // per processed channel: level thresholds (table-mode channels)
 
@@ -326,6 +327,7 @@ const double *input_lut(iwb200_job *job, std::vector<lut_key> &cache, int depth,
   for (int i = 0; i < n; i++) t[i] = iwb_to_linear(((double)i) / mx, &cs);
   const double *d = job->upload(t.data(), t.size());
   cache.push_back({maxcode, cs.cstype, cs.gamma, d});
+  if (n == 256) job->lut_host[d] = t;                            // host copy: the streaming kernels want it replicated
   return d;
 }
 
@@ -774,6 +776,14 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
       job->s2_store.reset(new iwb200_job::s2_tables());
       f->s2v = &job->s2_store->v; f->s2h = &job->s2_store->h; f->q2 = job->s2_store->q;
       bool ok = upload_sched2(job, hv, job->in_h, job->out.height, f->s2v) && upload_sched2(job, hh, job->in_w, job->out.width, f->s2h);
+      {
+        std::vector<double> rep(256 * 16);                      // the vertical kernel's shared-memory table, ready to bulk-copy
+        const std::vector<double> &src = job->lut_host[f->lut];
+        ok = ok && src.size() == 256;
+        for (int i = 0; ok && i < 256 * 16; i++) rep[i] = src[i >> 4];
+        f->lut16 = job->upload(rep.data(), rep.size());
+        ok = ok && f->lut16 != nullptr;
+      }
       f->same_tables = 1;
       for (int p = 0; p < nch && ok; p++) {
         if (f->epi == 2) {                                       // cells between the nearest-colour midpoints (one table for all)
@@ -850,7 +860,7 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
       hp.sh = iwb2_h_shift(hj);            // where the horizontal pass wants column 0 (16-byte aligned TMA tiles)
       V2Job vj{};
       V2Params &vp = vj.p;
-      vp.src = src0; vp.bpr = in.bpr; vp.ncols = job->in_w * nch; vp.lut = f->lut; vp.sc = *f->s2v;
+      vp.src = src0; vp.bpr = in.bpr; vp.ncols = job->in_w * nch; vp.lut16 = f->lut16; vp.sc = *f->s2v;
       vp.tm_row0 = f->vfirst[c0]; vp.tm_rows = f->vlast[c1 - 1] - f->vfirst[c0] + 1;
       vp.inter = inter; vp.pitch = (int)pitch; vp.sh = hp.sh; vp.row_base = c0; vp.row_lo = c0; vp.row_hi = c1;
       vj.S = f->SV; vj.first_host = f->vfirst.data(); vj.last_host = f->vlast.data(); vj.strip_override = f->strip2; vj.allow_uniform = f->uniform;

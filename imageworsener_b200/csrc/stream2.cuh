@@ -25,10 +25,10 @@
 #if !defined(IWB_EMU)
 
 #ifndef IWB2_V_WARPS
-#define IWB2_V_WARPS 6
+#define IWB2_V_WARPS 4
 #endif
 #ifndef IWB2_V_MINB
-#define IWB2_V_MINB 2            // resident CTAs per SM the register allocation aims at
+#define IWB2_V_MINB 4            // resident CTAs per SM the register allocation aims at (16 warps per SM)
 #endif
 #ifndef IWB2_V_G
 #define IWB2_V_G 8               // general path: input rows per stage
@@ -48,8 +48,15 @@
 #ifndef IWB2_U_NST
 #define IWB2_U_NST 2             // uniform path: stages (one cycle of S outputs each)
 #endif
-#ifndef IWB2_DEFER
-#define IWB2_DEFER 1             // deferred adds (stream2_dev.cuh); 0 trades them for registers / occupancy
+// Deferred adds (stream2_dev.cuh) make the FP64 instructions of one input independent of each other at the price
+// of one more register pair per accumulator.  Measured on cfg2: the vertical kernel (4 columns x S slots per thread)
+// is faster WITHOUT them at 16 warps per SM (0.117 ms) than with them at 12 (0.127 ms); the horizontal kernel, whose
+// occupancy is bounded by shared memory, keeps them.
+#ifndef IWB2_DEFER_V
+#define IWB2_DEFER_V 0
+#endif
+#ifndef IWB2_DEFER_H
+#define IWB2_DEFER_H 1
 #endif
 #ifndef IWB2_OST_PITCH
 #define IWB2_OST_PITCH 100       // bytes per output staging row (25 words, odd: lane-private banks); <= 96 bytes staged
@@ -96,7 +103,7 @@ struct V2Params {
   int tm_row0, tm_rows;          // input rows [tm_row0, tm_row0 + tm_rows) are in memory for this launch (TMA tensor extent)
   size_t bpr;                    // multiple of 16
   int ncols;                     // byte columns (= in_w * channels)
-  const double *lut;             // [256] code -> linear
+  const double *lut16;           // [256][16] code -> linear, every entry repeated 16 times (the shared-memory layout)
   Sched2 sc;
   float *inter;                  // row-major FP32 intermediate
   int pitch;                     // floats per row of `inter` (multiple of 4)

@@ -178,11 +178,20 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
         if (s < nstg) fill(s, s);
     }
   }
-  for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) lut_s[i] = p.lut[i >> 4];
+  // the colour table arrives already replicated 16 ways ([256][16] doubles = 32 KB) by one bulk copy
+  uint64_t *lbar = (uint64_t *)(last_s + ((nout + 1) & ~1));
+  if (threadIdx.x == 0) {
+    const unsigned lb = s2_addr(lbar);
+    s2_mbar_init(lb, 1);
+    s2_fence_async();
+    s2_mbar_expect(lb, 256 * 16 * 8);
+    s2_bulk_g2s(s2_addr(lut_s), p.lut16, 256 * 16 * 8, lb);
+  }
   if (!uni)
     for (int i = threadIdx.x; i < nout; i += blockDim.x) last_s[i] = p.sc.last[ob + i] - r0;
   __syncthreads();
   if (!active) return;
+  s2_mbar_wait(s2_addr(lbar), 0);
 
   double acc[S][4], prod[S][4];                                 // slot accumulators and deferred products
 #pragma unroll
@@ -207,7 +216,7 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
     for (int c = 0; c < 4; c++) {
 #pragma unroll
       for (int s = 0; s < S; s++) {
-        if (IWB2_DEFER) {
+        if (IWB2_DEFER_V) {
           acc[s][c] = __dadd_rn(acc[s][c], prod[s][c]);
           prod[s][c] = __dmul_rn(vc[c], (s & 1) ? w[s >> 1].y : w[s >> 1].x);
         } else {
@@ -225,7 +234,7 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
   const ptrdiff_t out_step = p.pitch;
   auto finish = [&](int k, int o) {
 #pragma unroll
-    for (int c = 0; c < 4; c++) if (IWB2_DEFER) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
+    for (int c = 0; c < 4; c++) if (IWB2_DEFER_V) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
     if (o >= o0 && o < o1) {                                    // emitted rows are consecutive: outp walks down the plane
       const float f0 = (float)acc[k][0], f1 = (float)acc[k][1], f2 = (float)acc[k][2], f3 = (float)acc[k][3];
       if (full) {
@@ -578,7 +587,7 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
     for (int c = 0; c < NCH; c++) {
 #pragma unroll
       for (int s = 0; s < S; s++) {
-        if (IWB2_DEFER) {
+        if (IWB2_DEFER_H) {
           acc[s][c] = __dadd_rn(acc[s][c], prod[s][c]);
           prod[s][c] = __dmul_rn(vc[c], (s & 1) ? w[s >> 1].y : w[s >> 1].x);
         } else {
@@ -601,7 +610,7 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
   // slot k is complete: add its pending products, quantise + dither, stage the bytes, restart the slot
   auto finish = [&](int k, int xo) {
 #pragma unroll
-    for (int c = 0; c < NCH; c++) if (IWB2_DEFER) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
+    for (int c = 0; c < NCH; c++) if (IWB2_DEFER_H) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
     if (xo >= xo0 && xo < xo1) {
       if (xo - staged_from >= FU) flush(xo);
       const unsigned dstb = ost_a + (xo - staged_from) * NCH;

@@ -141,7 +141,7 @@ static inline size_t iwb2_v_smem(int S, int step, int nout) {
   const size_t stage_u = ((size_t)gu * 128 + (size_t)gu * SS * 8 + 127) & ~(size_t)127;
   const size_t ring = std::max((size_t)IWB2_V_NST * stage, (size_t)IWB2_U_NST * stage_u);
   const size_t warp_bytes = (ring + 8 * 8 + 127) & ~(size_t)127;
-  return 256 * 16 * 8 + IWB2_V_WARPS * warp_bytes + (size_t)nout * 4 + 16;
+  return 256 * 16 * 8 + IWB2_V_WARPS * warp_bytes + (size_t)((nout + 1) & ~1) * 4 + 16 + 16;
 }
 static inline size_t iwb2_h_smem(int S, int step, int nch, int ntab, int nout) {
   const int SS = (S + 1) & ~1;
