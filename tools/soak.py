@@ -1,0 +1,54 @@
+"""Soak test of the fast path against the reference build (on the GPU box): many seeded near-integer geometries
+plus full-size 8K images with every fast dither.  Prints one summary line per group; exit code 1 on any difference.
+
+    python tools/soak.py [n_random_cases]
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from imageworsener_b200 import configs, libimagew as L  # noqa: E402
+from test_stream2 import _near_integer_case  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+    prod, ref = L.load_product(), L.load_reference()
+    bad = samples = 0
+    t0 = time.time()
+    for seed in range(5000, 5000 + n):
+        cfg = _near_integer_case(seed)
+        nch = L.imgtype_num_channels(cfg.imgtype)
+        tight = configs.synth_rows(prod, cfg, seed=0x777 + seed)
+        bpr = (cfg.in_w * nch + 15) // 16 * 16
+        rows = np.full((cfg.in_h, bpr), 0x5A, np.uint8)
+        rows[:, : cfg.in_w * nch] = tight
+        _, b = configs.run_host(ref, cfg, tight)
+        for opts in ({}, {"cuda:uniform": 0}, {"cuda:gen": 1}):
+            _, a = configs.run_host(prod, cfg, rows, options=opts)
+            nd = int(np.count_nonzero(a != b))
+            samples += a.size
+            if nd:
+                bad += 1
+                print(f"DIFF seed {seed} {opts} {cfg.args!r} {cfg.in_w}x{cfg.in_h}: {nd} bytes", flush=True)
+    print(f"random near-integer geometries: {n} cases x 3 variants, {samples} output bytes compared, {bad} cases differ, {time.time() - t0:.0f} s", flush=True)
+    big = 0
+    for dither in ("-dither o", "-dither r", "", "-dither halftone"):
+        for flt, ow, oh in (("lanczos", 3840, 2160), ("catrom", 2560, 1440), ("mitchell", 3833, 2160)):
+            cfg = configs.Config("big", 7680, 4320, L.IW_IMGTYPE_RGB, 8, ow, oh, f"-width {ow} -height {oh} -filter {flt} {dither}")
+            rows = configs.synth_rows(prod, cfg, seed=0xABCDEF + ow)
+            _, a = configs.run_host(prod, cfg, rows)
+            _, b = configs.run_host(ref, cfg, rows)
+            nd = int(np.count_nonzero(a != b))
+            big += nd
+            print(f"8K {flt} -> {ow}x{oh} [{dither or 'no dither'}]: {nd} differing bytes of {a.size}", flush=True)
+    return 1 if (bad or big) else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
