@@ -3,6 +3,8 @@
 #pragma once
 #include <algorithm>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "stream2_dev.cuh"
 
@@ -59,13 +61,25 @@ static inline int iwb2_sm_count() {
   return sms[dev];
 }
 
-// Resident CTAs per SM of a kernel at a given dynamic shared-memory size (also raises the kernel's limit).
+// Resident CTAs per SM of a kernel at a given dynamic shared-memory size (also raises the kernel's limit).  Cached
+// per (device, kernel, size): the query costs microseconds of host time, which matters for small images.
 template <class K>
 static int iwb2_ctas_per_sm(K kernel, int threads, size_t smem) {
+  struct entry { const void *fn; int dev; size_t smem; int n; };
+  static std::mutex mu;
+  static std::vector<entry> cache;
+  const void *fn = (const void *)kernel;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  for (const entry &e : cache)
+    if (e.fn == fn && e.dev == dev && e.smem == smem) return e.n;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   int n = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess) n = 1;
-  return n < 1 ? 1 : n;
+  n = n < 1 ? 1 : n;
+  cache.push_back({fn, dev, smem, n});
+  return n;
 }
 
 // Split outputs [lo, hi) into parts.  `first` / `last` = host copies of the schedule's windows, `base`/`align`: part
