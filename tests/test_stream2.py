@@ -130,3 +130,22 @@ def test_fast_path_near_integer_factors_match_reference(prod, ref, seed):
         _, a = configs.run_host(prod, cfg, rows, options=opts)
         nd = int(np.count_nonzero(a != b))
         assert nd == 0, f"{cfg.args!r} {cfg.in_w}x{cfg.in_h} {opts}: {nd} differing bytes of {a.size}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra,opts", [
+    ("-filter lanczos -dither o", {"cuda:chunk_mb": 1}),          # many chunks of output rows per pass
+    ("-filter catrom -dither r", {"cuda:chunk_mb": 1}),           # ... with absolute PRNG coordinates
+    ("-filter lanczos -dither o -negate", {}),                    # post kernel behind the horizontal pass
+    ("-filter lanczos -dither o -crop 32,10,800,500", {}),        # crop origin on a 16-byte boundary (TMA kernels)
+    ("-filter lanczos -dither o -crop 33,11,801,499", {}),        # ... and off it (generation-1 kernels)
+    ("-filter mitchell -crop 64,0,640,768", {"cuda:chunk_mb": 1}),
+], ids=["chunks", "chunks-random", "negate", "crop-aligned", "crop-unaligned", "crop-chunks"])
+def test_fast_path_chunks_negate_crop(prod, ref, extra, opts):
+    ow, oh = (512, 384) if "-crop" not in extra else (400, 250)
+    cfg = configs.Config("misc", 1024, 768, RGB, 8, ow, oh, f"-width {ow} -height {oh} {extra}")
+    rows = configs.synth_rows(prod, cfg)
+    _, a = configs.run_host(prod, cfg, rows, options=opts)
+    _, b = configs.run_host(ref, cfg, rows)
+    nd = int(np.count_nonzero(a != b))
+    assert nd == 0, f"{nd} differing bytes of {a.size}"
