@@ -6,6 +6,7 @@
 // vertical pass that writes it and the horizontal pass that reads it; the output is written in its final
 // interleaved byte layout.  Chunks are processed in order on one stream.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -26,7 +27,7 @@
 // Thin device layer.  The product build is CUDA only.  -DIWB_EMU (tests/_emu, never shipped, never loaded by the
 // package) swaps it for plain host memory + a loop so host logic can be debugged on a machine without a GPU.
 // ------------------------------------------------------------------------------------------------------
-static unsigned long long g_launches = 0;
+static std::atomic<unsigned long long> g_launches{0};   // (contexts may run concurrently from several threads)
 
 #if !defined(IWB_EMU)
 #include <cuda_runtime.h>
@@ -1015,7 +1016,7 @@ const char *iwb200_version(void) {
   return "imagew_b200 0.1 sm_100a";
 #endif
 }
-unsigned long long iwb200_kernel_launch_count(void) { return g_launches; }
+unsigned long long iwb200_kernel_launch_count(void) { return g_launches.load(); }
 const char *iwb200_job_last_error(const iwb200_job *job) { return job ? job->err.c_str() : "null job"; }
 
 void iwb200_job_destroy(iwb200_job *job) {
