@@ -98,6 +98,7 @@ struct FastPlan {
   int same_tables = 0;
   int strip2 = 0, seg2 = 0;                        // 0: sized per launch to one wave of CTAs
   int uniform = 1;
+  int depth16 = 0;                                 // 16-bit big-endian input (generation 2 only)
   int overlap = 1;                                 // sub-chunks pipelined over two streams (V of i+1 beside H of i)
   void *aux_stream = nullptr;
   std::vector<void *> ev;                          // [0..63] V done, [64..127] H done, [128] entry

@@ -623,7 +623,10 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
   iw_context *ctx = job->ctx;
   f->enabled = 0;
   const int nch = ctx->in_nch_phys;
-  if (ctx->img1.sampletype != IW_SAMPLETYPE_UINT || ctx->img1.bit_depth != 8) return;
+  // 8-bit input: both generations of streaming kernels; 16-bit input: generation 2 only (its table stays in L2)
+  const bool d16 = ctx->img1.bit_depth == 16;
+  if (ctx->img1.sampletype != IW_SAMPLETYPE_UINT || (ctx->img1.bit_depth != 8 && !d16)) return;
+  f->depth16 = d16 ? 1 : 0;
   if ((ctx->img1.orient_transform & 7) != 0) return;
   if (nch != 1 && nch != 3) return;
   if (ctx->in_type_logical != ctx->img1.imgtype) return;
@@ -777,7 +780,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
       job->s2_store.reset(new iwb200_job::s2_tables());
       f->s2v = &job->s2_store->v; f->s2h = &job->s2_store->h; f->q2 = job->s2_store->q;
       bool ok = upload_sched2(job, hv, job->in_h, job->out.height, f->s2v) && upload_sched2(job, hh, job->in_w, job->out.width, f->s2h);
-      {
+      if (!d16) {
         std::vector<double> rep(256 * 16);                      // the vertical kernel's shared-memory table, ready to bulk-copy
         const std::vector<double> &src = job->lut_host[f->lut];
         ok = ok && src.size() == 256;
@@ -803,6 +806,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
       f->v2 = ok ? 1 : 0;
     }
   }
+  if (d16 && !f->v2) f->enabled = 0;                             // no first-generation kernels for 16-bit input
 }
 
 static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const DevOutput &out, int r0, int r1,
@@ -817,7 +821,7 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
   }
   const int nch = f->nch;
   // second-generation kernels: TMA needs 16-byte aligned rows
-  const uint8_t *src0 = in.pix + (ptrdiff_t)(in.y0 - in.row_origin) * (ptrdiff_t)in.bpr + (size_t)in.x0 * nch;
+  const uint8_t *src0 = in.pix + (ptrdiff_t)(in.y0 - in.row_origin) * (ptrdiff_t)in.bpr + (size_t)in.x0 * nch * (f->depth16 ? 2 : 1);
   if (f->v2 && in.bpr % 16 == 0 && ((uintptr_t)src0 & 15) == 0) {
     // The two kernels leave different units idle (V: FP64-heavy, H: latency-bound epilogue), so sub-chunks of
     // output rows are software-pipelined over two streams: H of sub-chunk i (auxiliary stream) runs beside V of
@@ -861,7 +865,7 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
       hp.sh = iwb2_h_shift(hj);            // where the horizontal pass wants column 0 (16-byte aligned TMA tiles)
       V2Job vj{};
       V2Params &vp = vj.p;
-      vp.src = src0; vp.bpr = in.bpr; vp.ncols = job->in_w * nch; vp.lut16 = f->lut16; vp.sc = *f->s2v;
+      vp.src = src0; vp.bpr = in.bpr; vp.ncols = job->in_w * nch; vp.lut16 = f->lut16; vp.lut64k = f->lut; vp.depth16 = f->depth16; vp.sc = *f->s2v;
       vp.tm_row0 = f->vfirst[c0]; vp.tm_rows = f->vlast[c1 - 1] - f->vfirst[c0] + 1;
       vp.inter = inter; vp.pitch = (int)pitch; vp.sh = hp.sh; vp.row_base = c0; vp.row_lo = c0; vp.row_hi = c1;
       vj.S = f->SV; vj.first_host = f->vfirst.data(); vj.last_host = f->vlast.data(); vj.strip_override = f->strip2; vj.allow_uniform = f->uniform;
@@ -1333,7 +1337,12 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
   out.pix = (uint8_t *)d_out; out.bpr = out_bpr; out.row_origin = r0;
 
 #if !defined(IWB_EMU)
-  if (job->fused.enabled) {
+  bool fast = job->fused.enabled != 0;
+  if (fast && job->fused.depth16) {                             // 16-bit input has only the TMA kernels: rows must be 16-byte aligned
+    const uint8_t *s0 = in.pix + (ptrdiff_t)(in.y0 - in.row_origin) * (ptrdiff_t)in.bpr + (size_t)in.x0 * job->fused.nch * 2;
+    fast = job->fused.v2 && in.bpr % 16 == 0 && ((uintptr_t)s0 & 15) == 0;
+  }
+  if (fast) {
     if (!fused_run(job, &job->fused, in, out, r0, r1, stream)) return 0;
     return 1;
   }

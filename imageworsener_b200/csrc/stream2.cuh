@@ -102,8 +102,10 @@ struct V2Params {
   const uint8_t *src;            // byte (row r, column c) of the cropped input is src[r * bpr + c]; 16-byte aligned
   int tm_row0, tm_rows;          // input rows [tm_row0, tm_row0 + tm_rows) are in memory for this launch (TMA tensor extent)
   size_t bpr;                    // multiple of 16
-  int ncols;                     // byte columns (= in_w * channels)
-  const double *lut16;           // [256][16] code -> linear, every entry repeated 16 times (the shared-memory layout)
+  int ncols;                     // sample columns (= in_w * channels)
+  const double *lut16;           // 8-bit input: [256][16] code -> linear, every entry repeated 16 times (the shared-memory layout)
+  const double *lut64k;          // 16-bit input: [65536] code -> linear (stays in global memory)
+  int depth16;                   // samples are 16-bit big-endian
   Sched2 sc;
   float *inter;                  // row-major FP32 intermediate
   int pitch;                     // floats per row of `inter` (multiple of 4)

@@ -96,17 +96,22 @@ __device__ __forceinline__ void s2_decode_part(const Part2 &pt, int id, int lo, 
 // output rows; walks the input rows of the strip once.  Loads run ahead of the arithmetic: while row i is
 // multiplied, the table values of row i+1 and the ring word of row i+2 are already in flight.
 // ---------------------------------------------------------------------------------------------------------
-template <int S, int STEP, int SH>
+// D16: the input samples are 16-bit big-endian (a warp's 128 columns are 256 bytes per row) and the code ->
+// linear table has 65 536 entries: it stays in global memory (L2-resident, read-only path) instead of being
+// replicated in shared memory.
+template <int S, int STEP, int SH, bool D16>
 __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
     iwb_v2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_u, const V2Params p) {
   constexpr int SS = (S + 1) & ~1;
   // general path: rows per stage, stages.  A general-only kernel (non-integer factors: the whole image takes this
   // path) gets a deeper pipeline than the general parts of a uniform launch (a few border rows).
   constexpr int G = iwb2_v_g(STEP), NST = IWB2_V_NST;
-  constexpr int STAGE = G * 128 + G * SS * 8;                   // bytes: input rows, then weights
+  constexpr int TW = D16 ? 256 : 128;                           // bytes of a warp's 128 columns in one input row
+  constexpr int LUTB = D16 ? 0 : 256 * 16 * 8;                  // shared-memory colour table (8-bit input only)
+  constexpr int STAGE = G * TW + G * SS * 8;                    // bytes: input rows, then weights
   constexpr int GU = STEP > 0 ? S * STEP : 4, NSTU = IWB2_U_NST;   // uniform path: one cycle per stage
   constexpr int STEPQ = STEP > 0 ? STEP : 1;
-  constexpr int STAGE_U = (GU * 128 + GU * SS * 8 + 127) & ~127;
+  constexpr int STAGE_U = (GU * TW + GU * SS * 8 + 127) & ~127;
   constexpr int RING = NST * STAGE > NSTU * STAGE_U ? NST * STAGE : NSTU * STAGE_U;
   constexpr int WARP_BYTES = (RING + 8 * 8 + 127) & ~127;       // TMA tiles land on 128-byte boundaries
   static_assert(G >= 4 && NST >= 3 && GU >= 4 && NSTU >= 2, "pipeline depth");
@@ -119,9 +124,9 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
   if (STEP == 0) uni = false;
 
   double *lut_s = (double *)smem_raw;                           // [256][16]
-  unsigned char *wbase = smem_raw + 256 * 16 * 8 + (size_t)warp * WARP_BYTES;
+  unsigned char *wbase = smem_raw + LUTB + (size_t)warp * WARP_BYTES;
   const unsigned bar0 = s2_addr(wbase + RING);
-  int *last_s = (int *)(smem_raw + 256 * 16 * 8 + (size_t)IWB2_V_WARPS * WARP_BYTES);   // general path: [nout]
+  int *last_s = (int *)(smem_raw + LUTB + (size_t)IWB2_V_WARPS * WARP_BYTES);   // general path: [nout]
   const int wcol0 = (blockIdx.x * IWB2_V_WARPS + warp) * 128;
   const bool active = wcol0 < p.ncols;
   const unsigned ring0 = s2_addr(wbase);
@@ -148,17 +153,17 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
   auto fill = [&](int n, int slot) {
     if (s2_elect()) {
       const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE;
-      s2_mbar_expect(bar, G * 128 + G * SS * 8);
-      s2_tma_2d(dst, &tmap, wcol0, r0 + n * G - p.tm_row0, bar);
-      s2_bulk_g2s(dst + G * 128, p.sc.w + (ptrdiff_t)(r0 + n * G) * SS, G * SS * 8, bar);
+      s2_mbar_expect(bar, G * TW + G * SS * 8);
+      s2_tma_2d(dst, &tmap, wcol0 * (TW / 128), r0 + n * G - p.tm_row0, bar);
+      s2_bulk_g2s(dst + G * TW, p.sc.w + (ptrdiff_t)(r0 + n * G) * SS, G * SS * 8, bar);
     }
   };
   auto fill_u = [&](int n, int slot) {                          // uniform path: stage n = cycle n (+1 of overrun)
     if (s2_elect()) {
       const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE_U;
-      s2_mbar_expect(bar, GU * 128 + GU * SS * 8);
-      s2_tma_2d(dst, &tmap_u, wcol0, R0 + n * GU - p.tm_row0, bar);
-      s2_bulk_g2s(dst + GU * 128, p.sc.w + (ptrdiff_t)(R0 + n * GU) * SS, GU * SS * 8, bar);
+      s2_mbar_expect(bar, GU * TW + GU * SS * 8);
+      s2_tma_2d(dst, &tmap_u, wcol0 * (TW / 128), R0 + n * GU - p.tm_row0, bar);
+      s2_bulk_g2s(dst + GU * TW, p.sc.w + (ptrdiff_t)(R0 + n * GU) * SS, GU * SS * 8, bar);
     }
   };
   if (active) {                                                 // start the pipeline before the table loads
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
   }
   // the colour table arrives already replicated 16 ways ([256][16] doubles = 32 KB) by one bulk copy
   uint64_t *lbar = (uint64_t *)(last_s + ((nout + 1) & ~1));
-  if (threadIdx.x == 0) {
+  if (!D16 && threadIdx.x == 0) {
     const unsigned lb = s2_addr(lbar);
     s2_mbar_init(lb, 1);
     s2_fence_async();
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
     for (int i = threadIdx.x; i < nout; i += blockDim.x) last_s[i] = p.sc.last[ob + i] - r0;
   __syncthreads();
   if (!active) return;
-  s2_mbar_wait(s2_addr(lbar), 0);
+  if (!D16) s2_mbar_wait(s2_addr(lbar), 0);
 
   double acc[S][4], prod[S][4];                                 // slot accumulators and deferred products
 #pragma unroll
@@ -202,13 +207,27 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
   const unsigned lut_lane = (lane & 15) * 8;                    // this lane's bank pair: bits 3..6 of the table offset
   const char *lut_b = (const char *)lut_s;
   auto lut_at = [&](unsigned off) { return *(const double *)(lut_b + off); };   // (the table base folds into the LDS immediate)
-  auto lookup1 = [&](unsigned x, int c) {                       // code * 128 bytes (16 copies of 8 bytes) + lane copy
-    const unsigned sh = c == 0 ? (x << 7) : (x >> (8 * c - 7));
+  // a thread's 4 samples of one row: 4 bytes (8-bit) or 8 bytes (16-bit big-endian)
+  struct word { unsigned a, b; };
+  auto ring_word = [](unsigned addr) {
+    word x;
+    if (D16) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x.a), "=r"(x.b) : "r"(addr));
+    else { x.a = s2_lds32(addr); x.b = 0; }
+    return x;
+  };
+  auto lookup1 = [&](const word &x, int c) {
+    if (D16) {                                                  // bytes (hi, lo) of sample c -> code -> global table
+      const unsigned wv = c < 2 ? x.a : x.b;
+      const unsigned code = __byte_perm(wv, 0, (c & 1) ? 0x4423 : 0x4401);
+      return __ldg(p.lut64k + code);
+    }
+    // 8-bit: code * 128 bytes (16 copies of 8 bytes) + lane copy
+    const unsigned sh = c == 0 ? (x.a << 7) : (x.a >> (8 * c - 7));
     return lut_at((sh & 0x7f80u) | lut_lane);
   };
   // one input row: drain last row's products into the accumulators, form this row's products (deferred), and
   // replace each column's value by the next row's as soon as its products are formed
-  auto taps = [&](double (&vc)[4], unsigned xn, unsigned wrow) {
+  auto taps = [&](double (&vc)[4], const word &xn, unsigned wrow) {
     double2 w[SS / 2];
 #pragma unroll
     for (int s2 = 0; s2 < SS / 2; s2++) w[s2] = s2_ldsw(wrow + 16 * s2);
@@ -267,22 +286,22 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
     s2_mbar_wait(bar0, 0);
     double vc[4];
     {
-      const unsigned x0 = s2_lds32(ring0 + lane * 4);
+      const word x0 = ring_word(ring0 + lane * (TW / 32));
 #pragma unroll
       for (int c = 0; c < 4; c++) vc[c] = lookup1(x0, c);       // row 0
     }
-    unsigned xn = s2_lds32(ring0 + lane * 4 + 128);             // row 1
+    word xn = ring_word(ring0 + lane * (TW / 32) + TW);         // row 1
     for (int cyc = 0; cyc < ncyc; cyc++) {
       const int nslot = slot + 1 == NSTU ? 0 : slot + 1;
       const unsigned npar = nslot == 0 ? par ^ 1 : par;
-      const unsigned sb = ring0 + slot * STAGE_U + lane * 4, sbn = ring0 + nslot * STAGE_U + lane * 4;
-      const unsigned wb = ring0 + slot * STAGE_U + GU * 128;
+      const unsigned sb = ring0 + slot * STAGE_U + lane * (TW / 32), sbn = ring0 + nslot * STAGE_U + lane * (TW / 32);
+      const unsigned wb = ring0 + slot * STAGE_U + GU * TW;
       const int og = og0 + cyc * S;
 #pragma unroll
       for (int r = 0; r < GU; r++) {
         if (r == GU - 2) s2_mbar_wait(bar0 + 8 * nslot, npar);  // the last two rows prefetch from the next stage
-        const unsigned xcur = xn;
-        xn = s2_lds32(r + 2 < GU ? sb + (r + 2) * 128 : sbn + (r + 2 - GU) * 128);   // row r+2
+        const word xcur = xn;
+        xn = ring_word(r + 2 < GU ? sb + (r + 2) * TW : sbn + (r + 2 - GU) * TW);   // row r+2
         taps(vc, xcur, wb + r * SS * 8);                        // row r (values of row r+1 from xcur)
         if ((r + 1) % STEPQ == 0) finish((r + 1) / STEPQ - 1, og + (r + 1) / STEPQ - 1);
       }
@@ -301,9 +320,9 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
   int ld_stage = 0, ld_slot = 0, w_slot = 0;
   unsigned parity = 0;
   s2_mbar_wait(bar0, 0);
-  unsigned pin = ring0 + lane * 4;
-  unsigned pin_end = pin + G * 128;
-  unsigned pw = ring0 + G * 128;
+  unsigned pin = ring0 + lane * (TW / 32);
+  unsigned pin_end = pin + G * TW;
+  unsigned pw = ring0 + G * TW;
   unsigned pw_end = pw + G * SS * 8;
   auto advance_load = [&]() {                                   // the read position leaves stage ld_stage
     __syncwarp();
@@ -311,22 +330,22 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
     ld_stage++;
     if (++ld_slot == NST) { ld_slot = 0; parity ^= 1; }
     if (ld_stage < nstg) s2_mbar_wait(bar0 + 8 * ld_slot, parity);
-    pin = ring0 + ld_slot * STAGE + lane * 4;
-    pin_end = pin + G * 128;
+    pin = ring0 + ld_slot * STAGE + lane * (TW / 32);
+    pin_end = pin + G * TW;
   };
   auto next_word = [&]() {
-    const unsigned x = s2_lds32(pin);
-    pin += 128;
+    const word x = ring_word(pin);
+    pin += TW;
     if (pin == pin_end) advance_load();
     return x;
   };
   double vc[4];
   {
-    const unsigned x0 = next_word();
+    const word x0 = next_word();
 #pragma unroll
     for (int c = 0; c < 4; c++) vc[c] = lookup1(x0, c);         // row 0
   }
-  unsigned xn = next_word();                                    // row 1
+  word xn = next_word();                                        // row 1
   int i = 0;                                                    // row being consumed (relative to r0)
   auto row_step = [&]() {
     taps(vc, xn, pw);
@@ -334,7 +353,7 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
     pw += SS * 8;
     if (pw == pw_end) {
       if (++w_slot == NST) w_slot = 0;
-      pw = ring0 + w_slot * STAGE + G * 128;
+      pw = ring0 + w_slot * STAGE + G * TW;
       pw_end = pw + G * SS * 8;
     }
     i++;

@@ -22,6 +22,8 @@ CASES = [
     ("odd_catrom_gray", 500, 333, GRAY, 8, 217, 140, "-filter catrom -dither r", {}),
     ("up_mitchell_rgb", 200, 150, RGB, 8, 320, 260, "-filter mitchell", {}),
     ("gray16_generic", 300, 200, GRAY, 16, 150, 100, "-filter catrom -dither r", {}),
+    ("gray16_stream", 320, 200, GRAY, 16, 160, 100, "-filter catrom -grayscale -dither r", {}),
+    ("rgb16_stream", 320, 200, RGB, 16, 150, 101, "-filter lanczos -dither o", {}),
 ]
 
 

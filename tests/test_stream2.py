@@ -149,3 +149,32 @@ def test_fast_path_chunks_negate_crop(prod, ref, extra, opts):
     _, b = configs.run_host(ref, cfg, rows)
     nd = int(np.count_nonzero(a != b))
     assert nd == 0, f"{nd} differing bytes of {a.size}"
+
+
+SHAPES16 = [
+    ("gray16_down2_catrom_r", 1024, 768, GRAY, 512, 384, "-filter catrom -grayscale -dither r"),
+    ("gray16_down2_lanczos_o", 1024, 768, GRAY, 512, 384, "-filter lanczos -grayscale -dither o"),
+    ("rgb16_down2_lanczos_o", 1024, 512, RGB, 512, 256, "-filter lanczos -dither o"),
+    ("rgb16_odd_mitchell", 1000, 512, RGB, 617, 300, "-filter mitchell"),
+    ("gray16_up_hermite", 320, 240, GRAY, 512, 400, "-filter hermite -grayscale -dither halftone"),
+    ("gray16_unaligned_stride", 1001, 400, GRAY, 500, 200, "-filter catrom -grayscale -dither r"),     # generic kernels
+    ("rgb16_down3_lanczos2", 1536, 480, RGB, 512, 160, "-filter lanczos2 -dither r"),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", SHAPES16, ids=[s[0] for s in SHAPES16])
+@pytest.mark.parametrize("variant", ["gen2", "gen2-general", "generic"])
+def test_fast_path_16bit_input_matches_reference(prod, ref, shape, variant):
+    """16-bit big-endian input (8-bit output): the vertical kernel's 16-bit variant (global 65 536-entry table) with
+    the same horizontal kernels; an input gamma as in BASELINE cfg5 for the gray cases."""
+    name, iw, ih, typ, ow, oh, extra = shape
+    cfg = configs.Config(name, iw, ih, typ, 16, ow, oh, f"-width {ow} -height {oh} {extra}",
+                         input_cs=("gamma", 2.2) if typ == GRAY else None)
+    rows = configs.synth_rows(prod, cfg)
+    opts = {"gen2": {}, "gen2-general": {"cuda:uniform": 0}, "generic": {"cuda:fused": 0}}[variant]
+    ia, a = configs.run_host(prod, cfg, rows, options=opts)
+    ib, b = configs.run_host(ref, cfg, rows)
+    assert (ia.width, ia.height, ia.bit_depth, ia.imgtype, ia.bpr) == (ib.width, ib.height, ib.bit_depth, ib.imgtype, ib.bpr)
+    nd = int(np.count_nonzero(a != b))
+    assert nd == 0, f"{nd} differing bytes of {a.size}"
