@@ -666,14 +666,6 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
   if (const char *o = iwb_option(ctx, "cuda:strip")) f->strip = std::max(8, atoi(o) & ~7);
   if (const char *o = iwb_option(ctx, "cuda:seg")) f->seg = std::max(4, atoi(o) & ~3);
   // shared-memory needs: longest input range of any strip / segment
-  auto longest = [](const std::vector<int> &first, const std::vector<int> &last, int step) {
-    int m = 0, n = (int)first.size();
-    for (int o0 = 0; o0 < n; o0 += step) {
-      int o1 = std::min(n, o0 + step);
-      m = std::max(m, last[o1 - 1] - first[o0] + 1);
-    }
-    return m;
-  };
   // strips restart at every chunk boundary, so bound by any window of `strip` consecutive outputs
   auto longest_any = [](const std::vector<int> &first, const std::vector<int> &last, int step) {
     int m = 0, n = (int)first.size();
@@ -683,7 +675,6 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
     }
     return m;
   };
-  (void)longest;
   while (true) {
     f->v_nr_max = longest_any(hv.first, hv.last, f->strip);
     f->v_smem = v_smem_bytes(f->v_nr_max, f->SV, f->strip + f->SV, f->NC);

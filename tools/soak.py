@@ -37,6 +37,27 @@ def main():
                 bad += 1
                 print(f"DIFF seed {seed} {opts} {cfg.args!r} {cfg.in_w}x{cfg.in_h}: {nd} bytes", flush=True)
     print(f"random near-integer geometries: {n} cases x 3 variants, {samples} output bytes compared, {bad} cases differ, {time.time() - t0:.0f} s", flush=True)
+    # the same geometries with 16-bit big-endian input (rows of 16-bit samples padded to 16 bytes)
+    bad16 = samples16 = 0
+    for seed in range(9000, 9000 + n // 2):
+        c8 = _near_integer_case(seed)
+        cfg = configs.Config(c8.name, c8.in_w, c8.in_h, c8.imgtype, 16, c8.out_w, c8.out_h, c8.args,
+                             input_cs=("gamma", 2.2) if seed % 3 == 0 else None)
+        nch = L.imgtype_num_channels(cfg.imgtype)
+        tight = configs.synth_rows(prod, cfg, seed=0x999 + seed)
+        bpr = (cfg.in_w * nch * 2 + 15) // 16 * 16
+        rows = np.full((cfg.in_h, bpr), 0x5A, np.uint8)
+        rows[:, : cfg.in_w * nch * 2] = tight
+        _, b = configs.run_host(ref, cfg, tight)
+        for opts in ({}, {"cuda:uniform": 0}):
+            _, a = configs.run_host(prod, cfg, rows, options=opts)
+            nd = int(np.count_nonzero(a != b))
+            samples16 += a.size
+            if nd:
+                bad16 += 1
+                print(f"DIFF16 seed {seed} {opts} {cfg.args!r} {cfg.in_w}x{cfg.in_h}: {nd} bytes", flush=True)
+    print(f"16-bit input: {n // 2} cases x 2 variants, {samples16} output bytes compared, {bad16} cases differ", flush=True)
+    bad += bad16
     big = 0
     for dither in ("-dither o", "-dither r", "", "-dither halftone"):
         for flt, ow, oh in (("lanczos", 3840, 2160), ("catrom", 2560, 1440), ("mitchell", 3833, 2160)):
