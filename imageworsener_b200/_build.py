@@ -60,8 +60,6 @@ def build_product(force: bool = False, verbose_ptxas: bool = False, out: str | N
     time), then linked into one shared library.  IWB_QUICK=1 in the environment builds only the kernel variants
     of the headline configuration (tuning builds; never committed or shipped that way)."""
     target = out or PRODUCT_SO
-    if not force and _newer(target, _all_deps()):
-        return target
     from concurrent.futures import ThreadPoolExecutor
     obj_dir = OBJ_DIR if not out else OBJ_DIR + "_" + os.path.splitext(os.path.basename(out))[0]
     os.makedirs(obj_dir, exist_ok=True)
@@ -74,6 +72,13 @@ def build_product(force: bool = False, verbose_ptxas: bool = False, out: str | N
         flags.append("-DIWB_QUICK=1")
     for d in os.environ.get("IWB_DEFS", "").split():
         flags.append("-D" + d)
+    # the library remembers how it was built: a tuning build (IWB_QUICK / IWB_DEFS) left in the tree must never be
+    # mistaken for the product
+    stamp = target + ".flags"
+    flavour = " ".join(flags)
+    same = os.path.exists(stamp) and open(stamp).read() == flavour
+    if not force and same and _newer(target, _all_deps()):
+        return target
     if verbose_ptxas:
         flags.append("-Xptxas=-v")
 
@@ -86,6 +91,8 @@ def build_product(force: bool = False, verbose_ptxas: bool = False, out: str | N
         objs = list(ex.map(compile_one, DEVICE_SOURCES + HOST_SOURCES))
     _run([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-shared",
           "-Xlinker", "-Bsymbolic", "-o", target] + objs)
+    with open(stamp, "w") as fh:
+        fh.write(flavour)
     return target
 
 
