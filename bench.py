@@ -114,6 +114,32 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, BEFORE any page-locked buffer is allocated
+    (first touch puts the pages there): with several ranks per box the host-to-device copies of the end-to-end
+    leg otherwise cross the socket interconnect.  Best effort; returns a short description for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(gpu_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(gpu_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "no NUMA information"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"node {node} ({len(cpus)} cpus)"
+    except Exception as e:  # noqa: BLE001
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
 def make_ctx(lib: L.Lib, cfg, rows=None, options=None):
     ctx = lib.iw_create_context(None)
     if cfg.max_malloc:
@@ -208,6 +234,7 @@ def main():
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -399,7 +426,7 @@ def main():
                            "sharding": ("one image split into output-row bands, gathered to rank 0 with NCCL" if band_mode else
                                         "one image per GPU, no data-path collective") if world > 1 else "single GPU",
                            "l2_defeat": f"{nbuf} rotating input/output buffer sets ({nbuf * (cfg.in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2)",
-                           "fused_kernel": bool(info.uses_fused_kernel)},
+                           "fused_kernel": bool(info.uses_fused_kernel), "host_numa_binding": numa},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
