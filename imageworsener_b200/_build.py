@@ -103,7 +103,7 @@ def build_emulator(force: bool = False) -> str:
     srcs = [os.path.join(CSRC, f) for f in HOST_SOURCES]
     cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden",
            "-Wl,-Bsymbolic", "-DIWB_EMU=1", "-DIWB_BUILDING=1", "-Wall", "-o", EMU_SO] + srcs
-    cmd += ["-x", "c++", os.path.join(CSRC, "pipeline.cu")]   # kernel bodies as host loops (stream2.cu is device-only)
+    cmd += ["-x", "c++", os.path.join(CSRC, "pipeline.cu")]   # kernel bodies as host loops (the stream2_*.cu units are device-only)
     _run(cmd)
     return EMU_SO
 
