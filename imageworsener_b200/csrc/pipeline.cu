@@ -1488,7 +1488,13 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
   if (!iwb200_job_band_input_rows(job, r0, r1, &first, &last)) return fail(job, "invalid output row band");
   first = std::max(first, 0);
   last = std::min(last, job->phys_h - 1);
-  const size_t in_bytes = (size_t)(last - first + 1) * in_bpr;
+  // The device copy of the input gets a row pitch that is a multiple of 16 bytes (the TMA kernels need aligned rows);
+  // the pitch conversion costs nothing: it is done by the copy engine (2-D H2D copy).
+  size_t d_bpr = in_bpr;
+#if !defined(IWB_EMU)
+  if (job->fused.enabled && job->fused.v2 && in_bpr % 16 != 0 && !iwb_option(job->ctx, "cuda:keep_pitch")) d_bpr = (in_bpr + 15) & ~(size_t)15;
+#endif
+  const size_t in_bytes = (size_t)(last - first + 1) * d_bpr;
   const size_t out_bytes = (size_t)(r1 - r0) * out_bpr;
   if (job->d_in_bytes < in_bytes) { dev_free(job->d_in); job->d_in = dev_alloc(in_bytes, job->err); job->d_in_bytes = in_bytes; }
   if (job->d_out_bytes < out_bytes) { dev_free(job->d_out); job->d_out = dev_alloc(out_bytes, job->err); job->d_out_bytes = out_bytes; }
@@ -1541,13 +1547,19 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
     l = std::min(l, last);
     if (nsub == 1) l = last;
     if (l > copied_to) {
-      const size_t off = (size_t)(copied_to + 1 - first) * in_bpr, n = (size_t)(l - copied_to) * in_bpr;
-      ok = dev_h2d((uint8_t *)job->d_in + off, (const uint8_t *)h_in + (size_t)(copied_to + 1) * in_bpr, n, s_in, job->err);
+      const size_t off = (size_t)(copied_to + 1 - first) * d_bpr, n = (size_t)(l - copied_to) * in_bpr;
+      if (d_bpr == in_bpr) {
+        ok = dev_h2d((uint8_t *)job->d_in + off, (const uint8_t *)h_in + (size_t)(copied_to + 1) * in_bpr, n, s_in, job->err);
+      } else {
+        ok = cudaMemcpy2DAsync((uint8_t *)job->d_in + off, d_bpr, (const uint8_t *)h_in + (size_t)(copied_to + 1) * in_bpr, in_bpr, in_bpr,
+                               (size_t)(l - copied_to), cudaMemcpyHostToDevice, s_in) == cudaSuccess;
+        if (!ok) job->err = "H2D copy (2-D) failed";
+      }
       copied_to = l;
     }
     cudaEventRecord(ev(2 * k), s_in);
     cudaStreamWaitEvent(s_k, ev(2 * k), 0);
-    ok = ok && iwb200_job_run_device(job, job->d_in, in_bpr, first, (uint8_t *)job->d_out + (size_t)(b0 - r0) * out_bpr, out_bpr,
+    ok = ok && iwb200_job_run_device(job, job->d_in, d_bpr, first, (uint8_t *)job->d_out + (size_t)(b0 - r0) * out_bpr, out_bpr,
                                      b0, b1, s_k);
     cudaEventRecord(ev(2 * k + 1), s_k);
     cudaStreamWaitEvent(s_out, ev(2 * k + 1), 0);

@@ -178,3 +178,18 @@ def test_fast_path_16bit_input_matches_reference(prod, ref, shape, variant):
     assert (ia.width, ia.height, ia.bit_depth, ia.imgtype, ia.bpr) == (ib.width, ib.height, ib.bit_depth, ib.imgtype, ib.bpr)
     nd = int(np.count_nonzero(a != b))
     assert nd == 0, f"{nd} differing bytes of {a.size}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opts", [{}, {"cuda:keep_pitch": 1}], ids=["aligned-device-copy", "caller-pitch"])
+@pytest.mark.parametrize("depth", [8, 16])
+def test_fast_path_unaligned_host_rows(prod, ref, opts, depth):
+    """Host rows whose stride is not a multiple of 16 bytes: iw_process_image gives the device copy an aligned pitch
+    (2-D copy), so the TMA kernels run; with cuda:keep_pitch the device copy keeps the caller's stride and the
+    job falls back (generation 1 for 8-bit, generic kernels for 16-bit).  Same bytes either way."""
+    cfg = configs.Config("unal", 1001, 400, RGB, depth, 500, 200, "-width 500 -height 200 -filter lanczos -dither o")
+    rows = configs.synth_rows(prod, cfg)
+    assert rows.shape[1] % 16 != 0
+    _, a = configs.run_host(prod, cfg, rows, options=opts)
+    _, b = configs.run_host(ref, cfg, rows)
+    assert np.array_equal(a, b)
