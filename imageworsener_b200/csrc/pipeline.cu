@@ -394,9 +394,13 @@ struct HostSched {
   std::vector<int> emit_lo, emit_n, first, last;
 };
 
-// Turn a tap list into the per-input streaming schedule.  Only lists whose windows are contiguous runs of real
+// Turn a tap list into the per-input streaming schedule.  Only lists whose windows are increasing runs of real
 // source samples, non-empty and monotone qualify (the STANDARD edge policy away from degenerate cases);
 // anything else stays on the generic kernels.
+// A window may have holes: the reference drops taps whose weight is exactly zero (src/imagew-resize.c:302; a cubic
+// filter at |x| = 1 for odd integer reduction factors).  The schedule gives such an input the weight 0.0, as it
+// does for every input outside a slot's window, which leaves the sum bit-identical: an accumulator starts at +0.0
+// and a sum of two doubles is -0.0 only if both are, so it never holds -0.0, and x + (+-0.0) = x for any other x.
 bool build_sched(const iwb_axis_table &t, int max_slots, HostSched *hs) {
   if (t.mode != 0 || t.n_out < 1) return false;
   const int n_in = t.n_in, n_out = t.n_out;
@@ -407,7 +411,7 @@ bool build_sched(const iwb_axis_table &t, int max_slots, HostSched *hs) {
     if (b <= a) return false;
     if (t.src[a] < 0) return false;
     for (int k = a + 1; k < b; k++)
-      if (t.src[k] != t.src[k - 1] + 1) return false;
+      if (t.src[k] <= t.src[k - 1]) return false;
     hs->first[o] = t.src[a];
     hs->last[o] = t.src[b - 1];
     if (hs->last[o] >= n_in) return false;
@@ -1227,7 +1231,7 @@ static iwb200_job *job_build(iw_context *ctx, int device) {
 #if !defined(IWB_EMU)
   const char *nofuse = iwb_option(ctx, "cuda:fused");
   if (!(nofuse && !strcmp(nofuse, "0"))) fused_plan_build(job, &job->fused);
-  info.uses_fused_kernel = job->fused.enabled;
+  info.uses_fused_kernel = job->fused.enabled ? (job->fused.v2 ? 2 : 1) : 0;
 #endif
   job->flush_tables();
   return job;

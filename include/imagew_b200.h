@@ -303,7 +303,7 @@ struct iwb200_job_info {
   int in_width_phys, in_height_phys; /* physical (stored) rows/columns of the input buffer */
   size_t in_bpr;
   int bandable;             /* 0 when the job must run as one band (error-diffusion dither) */
-  int uses_fused_kernel;    /* 1 when the fused V+H tile kernel is selected for this job */
+  int uses_fused_kernel;    /* 0: generic per-sample kernels; 1 / 2: streaming kernels of the first / second generation */
   double taps_v, taps_h;    /* total filter taps (mul+add pairs) per full image, all channels */
 };
 

@@ -24,6 +24,12 @@ CASES = [
     ("gray16_generic", 300, 200, GRAY, 16, 150, 100, "-filter catrom -dither r", {}),
     ("gray16_stream", 320, 200, GRAY, 16, 160, 100, "-filter catrom -grayscale -dither r", {}),
     ("rgb16_stream", 320, 200, RGB, 16, 150, 101, "-filter lanczos -dither o", {}),
+    # cubic filters at odd integer factors: the reference drops the exactly-zero taps at |x| = 1, the streaming
+    # schedules carry a zero weight there instead (pipeline.cu:build_sched)
+    ("down3_catrom_holes", 480, 360, RGB, 8, 160, 120, "-filter catrom -dither o", {}),
+    ("down3_catrom_holes_general", 480, 360, RGB, 8, 160, 120, "-filter catrom -dither o", {"cuda:uniform": 0}),
+    ("down3_catrom_holes_gen1", 480, 360, RGB, 8, 160, 120, "-filter catrom -dither o", {"cuda:gen": 1}),
+    ("down5_mitchell_holes_gray16", 640, 400, GRAY, 16, 128, 80, "-filter mitchell -grayscale", {}),
 ]
 
 

@@ -37,6 +37,11 @@ SHAPES = [
     ("down4_hermite", 2048, 512, GRAY, 512, 128, "-filter hermite -dither r"),           # 2 open windows, step 4
     ("down4_quadratic", 2048, 512, RGB, 512, 128, "-filter quadratic"),                  # 3 open windows, step 4
     ("down2_triangle", 1024, 512, RGB, 512, 256, "-filter triangle -dither halftone"),   # 2 open windows, step 2
+    # windows with holes: taps whose weight is exactly zero are absent from the reference's lists
+    ("down3_catrom_holes", 1536, 960, RGB, 512, 320, "-filter catrom"),
+    ("down3_catrom_holes_r", 1536, 480, GRAY, 512, 160, "-filter catrom -grayscale -dither r"),
+    ("down5_mitchell_holes", 2560, 640, RGB, 512, 128, "-filter mitchell -dither o"),
+    ("up2_catrom_holes", 256, 200, RGB, 512, 400, "-filter catrom -dither o"),
 ]
 
 
@@ -193,3 +198,25 @@ def test_fast_path_unaligned_host_rows(prod, ref, opts, depth):
     _, a = configs.run_host(prod, cfg, rows, options=opts)
     _, b = configs.run_host(ref, cfg, rows)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [s for s in SHAPES if "holes" in s[0] and not s[0].startswith("up")], ids=lambda s: s[0])
+def test_windows_with_holes_take_the_streaming_kernels(prod, shape):
+    """Jobs whose tap lists skip zero-weight samples are planned onto the generation-2 kernels, not the generic ones."""
+    import ctypes as C
+    from test_intermediate import Info, _job_api
+    cfg = _cfg(shape)
+    rows = configs.synth_rows(prod, cfg)
+    dll = prod.dll
+    _job_api(dll)
+    ctx = prod.iw_create_context(None)
+    prod.set_input_from_numpy(ctx, rows, cfg.imgtype, cfg.bit_depth, cfg.in_w, cfg.in_h)
+    cfg.apply(prod, ctx)
+    job = dll.iwb200_job_create(ctx, 0)
+    assert job, prod.errmsg(ctx)
+    info = Info()
+    dll.iwb200_job_get_info(job, C.byref(info))
+    dll.iwb200_job_destroy(job)
+    prod.iw_destroy_context(ctx)
+    assert info.uses_fused_kernel == 2
