@@ -415,7 +415,16 @@ bool build_sched(const iwb_axis_table &t, int max_slots, HostSched *hs) {
     hs->first[o] = t.src[a];
     hs->last[o] = t.src[b - 1];
     if (hs->last[o] >= n_in) return false;
-    if (o && (hs->first[o] < hs->first[o - 1] || hs->last[o] < hs->last[o - 1])) return false;
+  }
+  // a zero tap dropped at an end of a list can make a window start after (end before) its neighbour's: widen such
+  // windows, again with zero weights, until starts and ends are monotone; real breaks of monotonicity stay generic
+  for (int o = n_out - 2; o >= 0; o--) {
+    if (hs->first[o] > hs->first[o + 1] + 1) return false;
+    hs->first[o] = std::min(hs->first[o], hs->first[o + 1]);
+  }
+  for (int o = 1; o < n_out; o++) {
+    if (hs->last[o] < hs->last[o - 1] - 1) return false;
+    hs->last[o] = std::max(hs->last[o], hs->last[o - 1]);
   }
   // most windows open at once
   int S = 1;

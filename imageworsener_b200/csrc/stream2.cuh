@@ -69,6 +69,9 @@
 __host__ __device__ constexpr int iwb2_v_g(int step) { return step > 0 ? IWB2_V_G : 2 * IWB2_V_G; }
 __host__ __device__ constexpr int iwb2_h_kp(int step) { return step > 0 ? IWB2_H_KP : 2 * IWB2_H_KP; }
 __host__ __device__ constexpr int iwb2_h_nst(int step) { return step > 0 ? IWB2_H_NST : IWB2_H_NST + 1; }
+// resident CTAs per SM the vertical kernel's register allocation aims at: 4 columns x S slots of FP64 accumulators
+// per thread leave room for IWB2_V_MINB CTAs up to 8 slots; enlargements (12 / 16 open windows) get the whole file
+__host__ __device__ constexpr int iwb2_v_minb(int S) { return S <= 8 ? IWB2_V_MINB : 2; }
 
 struct Sched2 {                  // device pointers
   const double *w;               // row r at w + r*SS, r in [-IWB2_WPAD, n_in + IWB2_WPAD); SS = S rounded up to even

@@ -100,7 +100,7 @@ __device__ __forceinline__ void s2_decode_part(const Part2 &pt, int id, int lo, 
 // linear table has 65 536 entries: it stays in global memory (L2-resident, read-only path) instead of being
 // replicated in shared memory.
 template <int S, int STEP, int SH, bool D16>
-__global__ void __launch_bounds__(32 * IWB2_V_WARPS, IWB2_V_MINB)
+__global__ void __launch_bounds__(32 * IWB2_V_WARPS, iwb2_v_minb(S))
     iwb_v2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_u, const V2Params p) {
   constexpr int SS = (S + 1) & ~1;
   // general path: rows per stage, stages.  A general-only kernel (non-integer factors: the whole image takes this
@@ -464,6 +464,7 @@ template <int S, int STEP, int NCH, int EPI>
 __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
     iwb_h2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_u, const H2Params p) {
   constexpr int SS = (S + 1) & ~1;
+  constexpr bool DEFER = IWB2_DEFER_H && S * NCH <= 24;         // (deferred adds double the accumulator registers)
   constexpr int KP = iwb2_h_kp(STEP), NST = iwb2_h_nst(STEP);   // (deeper for a general-only kernel, see iwb_v2)
   constexpr int TP = iwb2_tile_pitch(KP * NCH + 3);             // general path: floats per tile row (+3: start rounded down)
   static_assert((KP * NCH) % 4 == 0, "general stages advance by whole 16-byte chunks");
@@ -606,7 +607,7 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
     for (int c = 0; c < NCH; c++) {
 #pragma unroll
       for (int s = 0; s < S; s++) {
-        if (IWB2_DEFER_H) {
+        if (DEFER) {
           acc[s][c] = __dadd_rn(acc[s][c], prod[s][c]);
           prod[s][c] = __dmul_rn(vc[c], (s & 1) ? w[s >> 1].y : w[s >> 1].x);
         } else {
@@ -629,7 +630,7 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
   // slot k is complete: add its pending products, quantise + dither, stage the bytes, restart the slot
   auto finish = [&](int k, int xo) {
 #pragma unroll
-    for (int c = 0; c < NCH; c++) if (IWB2_DEFER_H) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
+    for (int c = 0; c < NCH; c++) if (DEFER) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
     if (xo >= xo0 && xo < xo1) {
       if (xo - staged_from >= FU) flush(xo);
       const unsigned dstb = ost_a + (xo - staged_from) * NCH;

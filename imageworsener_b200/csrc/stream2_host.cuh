@@ -12,11 +12,11 @@
 // horizontal kernel reads 16-byte chunks, and a stage must end on one for 1 and 3 channels alike), 4..IWB2_MAX_GU
 #ifdef IWB_QUICK
 #define IWB2_UNIFORM_PAIRS(X) X(6, 2)
-#define IWB2_GENERAL_S(X) X(6)
+#define IWB2_GENERAL_S(X) X(6) X(12)
 #else
 #define IWB2_UNIFORM_PAIRS(X) \
   X(2, 2) X(4, 2) X(6, 2) X(8, 2) X(4, 3) X(2, 4) X(3, 4) X(4, 4) X(4, 1) X(8, 1)
-#define IWB2_GENERAL_S(X) X(2) X(3) X(4) X(5) X(6) X(8)
+#define IWB2_GENERAL_S(X) X(2) X(3) X(4) X(5) X(6) X(8) X(12) X(16)
 #endif
 
 static inline bool iwb2_pair_built(int S, int step) {

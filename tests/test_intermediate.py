@@ -30,6 +30,8 @@ CASES = [
     ("down3_catrom_holes_general", 480, 360, RGB, 8, 160, 120, "-filter catrom -dither o", {"cuda:uniform": 0}),
     ("down3_catrom_holes_gen1", 480, 360, RGB, 8, 160, 120, "-filter catrom -dither o", {"cuda:gen": 1}),
     ("down5_mitchell_holes_gray16", 640, 400, GRAY, 16, 128, 80, "-filter mitchell -grayscale", {}),
+    ("up2_lanczos_s12", 200, 120, RGB, 8, 400, 240, "-filter lanczos -dither o", {}),
+    ("up4_mitchell_s16_gray16", 100, 80, GRAY, 16, 400, 320, "-filter mitchell -grayscale -dither r", {}),
 ]
 
 

@@ -42,6 +42,12 @@ SHAPES = [
     ("down3_catrom_holes_r", 1536, 480, GRAY, 512, 160, "-filter catrom -grayscale -dither r"),
     ("down5_mitchell_holes", 2560, 640, RGB, 512, 128, "-filter mitchell -dither o"),
     ("up2_catrom_holes", 256, 200, RGB, 512, 400, "-filter catrom -dither o"),
+    # enlargements: 12 and 16 open windows (general-only kernels)
+    ("up2_lanczos_s12", 320, 200, RGB, 640, 400, "-filter lanczos -dither o"),
+    ("up3_catrom_s12", 200, 150, RGB, 600, 450, "-filter catrom -dither r"),
+    ("up4_mitchell_s16", 160, 120, RGB, 640, 480, "-filter mitchell"),
+    ("up2p4_lanczos_s16_gray", 200, 160, GRAY, 480, 384, "-filter lanczos -grayscale -dither halftone"),
+    ("up4_down2_mixed", 160, 800, RGB, 640, 400, "-filter mitchell -dither o"),          # 16 windows across, 4 down
 ]
 
 
@@ -164,6 +170,8 @@ SHAPES16 = [
     ("gray16_up_hermite", 320, 240, GRAY, 512, 400, "-filter hermite -grayscale -dither halftone"),
     ("gray16_unaligned_stride", 1001, 400, GRAY, 500, 200, "-filter catrom -grayscale -dither r"),     # generic kernels
     ("rgb16_down3_lanczos2", 1536, 480, RGB, 512, 160, "-filter lanczos2 -dither r"),
+    ("rgb16_up2_lanczos_s12", 320, 200, RGB, 640, 400, "-filter lanczos -dither o"),
+    ("gray16_up4_mitchell_s16", 160, 120, GRAY, 640, 480, "-filter mitchell -grayscale -dither r"),
 ]
 
 
@@ -201,9 +209,10 @@ def test_fast_path_unaligned_host_rows(prod, ref, opts, depth):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [s for s in SHAPES if "holes" in s[0] and not s[0].startswith("up")], ids=lambda s: s[0])
+@pytest.mark.parametrize("shape", [s for s in SHAPES if "holes" in s[0] or "_s1" in s[0]], ids=lambda s: s[0])
 def test_windows_with_holes_take_the_streaming_kernels(prod, shape):
-    """Jobs whose tap lists skip zero-weight samples are planned onto the generation-2 kernels, not the generic ones."""
+    """Jobs whose tap lists skip zero-weight samples, and enlargements with up to 16 open windows, are planned onto
+    the generation-2 kernels, not the older ones."""
     import ctypes as C
     from test_intermediate import Info, _job_api
     cfg = _cfg(shape)
