@@ -77,6 +77,7 @@ struct HStreamParams {
 struct FastPlan {
   int enabled = 0;
   int nch = 0;
+  int nco = 0;                   // output channels: nch, or 3 for gray input written as RGB (generation 2 only)
   int SV = 0, SH = 0, NC = 0;
   AxisSched sv{}, sh{};
   std::vector<int> vfirst, vlast, hfirst, hlast;   // host copies for band planning / uniform-range detection

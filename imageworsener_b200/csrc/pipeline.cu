@@ -643,13 +643,17 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
   if ((ctx->img1.orient_transform & 7) != 0) return;
   if (nch != 1 && nch != 3) return;
   if (ctx->in_type_logical != ctx->img1.imgtype) return;
-  if (job->nproc != nch || ctx->out_nch != nch || job->has_alpha) return;
+  // gray input written as RGB (the reference's default for gray images, src/imagew-main.c:1676-1684): three processed
+  // channels that all read input channel 0 -- one intermediate plane, three output bytes (generation 2 only)
+  const bool rep = nch == 1 && job->nproc == 3 && ctx->out_nch == 3;
+  const int nco = rep ? 3 : nch;
+  if (job->nproc != nco || ctx->out_nch != nco || job->has_alpha) return;
   if (ctx->img2.sampletype != IW_SAMPLETYPE_UINT || ctx->img2.bit_depth != 8) return;
   if (job->any_errdiff || ctx->intclamp) return;
   if (ctx->axis[0].per_channel_tables || ctx->axis[1].per_channel_tables) return;
-  for (int p = 0; p < nch; p++) {
+  for (int p = 0; p < nco; p++) {
     const iwb_mid_channel &mc = ctx->mid_ci[job->mid_index[p]];
-    if (job->mid_index[p] != p || mc.in_channel != p || mc.out_channel != p || mc.to_gray || mc.premultiplied) return;
+    if (job->mid_index[p] != p || mc.in_channel != (rep ? 0 : p) || mc.out_channel != p || mc.to_gray || mc.premultiplied) return;
     if (job->cin[p].early_bkgd || job->cin[p].lut[0] != job->cin[0].lut[0] || !job->cin[p].lut[0]) return;
   }
   HostSched hv, hh;
@@ -664,6 +668,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
     if (const char *o = iwb_option(ctx, "cuda:nc")) { int v = atoi(o); if ((v == 4 && hv.S <= 8) || (v == 8 && hv.S <= 6)) f->NC = v; }
   }
   f->nch = nch;
+  f->nco = nco;
   f->SV = hv.S;
   f->SH = hh.S;
   const int ncols = job->in_w * nch;
@@ -704,7 +709,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
   if (!upload_sched(job, hv, job->in_h, job->out.height, &f->sv)) return;
   if (!upload_sched(job, hh, job->in_w, job->out.width, &f->sh)) return;
   f->lut = job->cin[0].lut[0];
-  for (int p = 0; p < nch; p++) {
+  for (int p = 0; p < nco; p++) {
     const DevChanOut &o = job->cout[p];
     FastQuant &q = f->fq[p];
     q = FastQuant();
@@ -754,7 +759,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
   // epilogue specialisation: all channels in the same fast mode and dither, else the run-time generic one
   {
     bool same = true;
-    for (int p = 1; p < nch; p++)
+    for (int p = 1; p < nco; p++)
       if (f->fq[p].mode != f->fq[0].mode || job->cout[p].dfamily != job->cout[0].dfamily ||
           job->cout[p].dsubtype != job->cout[0].dsubtype) same = false;
     f->epi = 0;
@@ -779,7 +784,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
   {
     const char *o = iwb_option(ctx, "cuda:gen");
     const bool want = !(o && atoi(o) == 1);
-    if (want && iwb2_supported(hv.S, hh.S, nch, f->epi) && iwb2_tensor_maps_available()) {
+    if (want && iwb2_supported(hv.S, hh.S, nch, nco, f->epi) && iwb2_tensor_maps_available()) {
       static_assert(sizeof(Sched2) > 0 && sizeof(Quant2) > 0, "stream2.cuh");
       job->s2_store.reset(new iwb200_job::s2_tables());
       f->s2v = &job->s2_store->v; f->s2h = &job->s2_store->h; f->q2 = job->s2_store->q;
@@ -793,7 +798,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
         ok = ok && f->lut16 != nullptr;
       }
       f->same_tables = 1;
-      for (int p = 0; p < nch && ok; p++) {
+      for (int p = 0; p < nco && ok; p++) {
         if (f->epi == 2) {                                       // cells between the nearest-colour midpoints (one table for all)
           std::vector<double> cells(1, 0.0);
           cells.insert(cells.end(), job->nc_host.begin(), job->nc_host.end());
@@ -807,10 +812,11 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
       if (const char *o2 = iwb_option(ctx, "cuda:seg2")) f->seg2 = std::max(4, atoi(o2) & ~3);
       if (const char *o2 = iwb_option(ctx, "cuda:uniform")) f->uniform = atoi(o2) != 0;
       if (const char *o2 = iwb_option(ctx, "cuda:overlap")) f->overlap = std::max(1, std::min(32, atoi(o2)));
+      if (rep && !f->same_tables) ok = false;                    // (one decision serves the three bytes unless the dither is random)
       f->v2 = ok ? 1 : 0;
     }
   }
-  if (d16 && !f->v2) f->enabled = 0;                             // no first-generation kernels for 16-bit input
+  if ((d16 || rep) && !f->v2) f->enabled = 0;                    // no first-generation kernels for 16-bit input / gray as RGB
 }
 
 static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const DevOutput &out, int r0, int r1,
@@ -863,8 +869,8 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
       H2Params &hp = hj.p;
       hp.inter = inter; hp.pitch = (int)pitch; hp.ncols = job->in_w * nch; hp.row_lo = c0; hp.row_hi = c1; hp.sc = *f->s2h;
       hp.out_w = out.width; hp.out = out; hp.same_tables = f->same_tables; hp.jump = job->d_jump;
-      for (int p = 0; p < 4; p++) { hp.ch[p] = job->cout[p < nch ? p : 0]; hp.q[p] = f->q2[p < nch ? p : 0]; }
-      hj.S = f->SH; hj.nch = nch; hj.epi = f->epi; hj.first_host = f->hfirst.data(); hj.last_host = f->hlast.data(); hj.seg_override = f->seg2; hj.allow_uniform = f->uniform;
+      for (int p = 0; p < 4; p++) { hp.ch[p] = job->cout[p < f->nco ? p : 0]; hp.q[p] = f->q2[p < f->nco ? p : 0]; }
+      hj.S = f->SH; hj.nch = nch; hj.nco = f->nco; hj.epi = f->epi; hj.first_host = f->hfirst.data(); hj.last_host = f->hlast.data(); hj.seg_override = f->seg2; hj.allow_uniform = f->uniform;
       hp.sh = 0;
       hp.sh = iwb2_h_shift(hj);            // where the horizontal pass wants column 0 (16-byte aligned TMA tiles)
       V2Job vj{};
@@ -1342,8 +1348,8 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
 
 #if !defined(IWB_EMU)
   bool fast = job->fused.enabled != 0;
-  if (fast && job->fused.depth16) {                             // 16-bit input has only the TMA kernels: rows must be 16-byte aligned
-    const uint8_t *s0 = in.pix + (ptrdiff_t)(in.y0 - in.row_origin) * (ptrdiff_t)in.bpr + (size_t)in.x0 * job->fused.nch * 2;
+  if (fast && (job->fused.depth16 || job->fused.nco != job->fused.nch)) {   // these have only the TMA kernels: rows must be 16-byte aligned
+    const uint8_t *s0 = in.pix + (ptrdiff_t)(in.y0 - in.row_origin) * (ptrdiff_t)in.bpr + (size_t)in.x0 * job->fused.nch * (job->fused.depth16 ? 2 : 1);
     fast = job->fused.v2 && in.bpr % 16 == 0 && ((uintptr_t)s0 & 15) == 0;
   }
   if (fast) {
@@ -1437,6 +1443,7 @@ int iwb200_job_read_intermediate(iwb200_job *job, int ch, float *dst, size_t cap
   }
 #if !defined(IWB_EMU)
   const int nch = job->fused.nch;
+  if (job->fused.nco != nch) ch = 0;                             // gray written as RGB: the three channels share one plane
   if (job->last_path == 2) {
     std::vector<float> tmp((size_t)nrows * job->last_pitch);
     if (!dev_d2h(tmp.data(), job->last_inter, tmp.size() * sizeof(float), 0, job->err) || !dev_sync(0, job->err)) return 0;

@@ -144,6 +144,7 @@ struct V2Job {
 struct H2Job {
   H2Params p;                    // everything but `part`
   int S, nch, epi;
+  int nco;                       // output channels: nch, or 3 for one gray channel written as RGB
   const int *first_host, *last_host;
   int seg_override;
   int allow_uniform;
@@ -153,6 +154,6 @@ bool iwb2_tensor_maps_available();
 bool iwb2_run_v(const V2Job &job, cudaStream_t st);   // false: no kernel variant / launch problem
 bool iwb2_run_h(const H2Job &job, cudaStream_t st);
 int iwb2_h_shift(const H2Job &job);                    // the column shift (0..3) this horizontal launch wants from the vertical one
-bool iwb2_supported(int SV, int SH, int nch, int epi);
+bool iwb2_supported(int SV, int SH, int nch, int nco, int epi);
 
 #endif  // !IWB_EMU

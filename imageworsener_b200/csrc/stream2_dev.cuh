@@ -460,7 +460,10 @@ static __device__ __noinline__ void h2_flush(const unsigned char *ost, uint8_t *
 // quarter-warp (the row-major intermediate is transposed for free by this access pattern).
 __host__ __device__ constexpr int iwb2_tile_pitch(int k) { return (((k + 3) / 4) | 1) * 4; }
 
-template <int S, int STEP, int NCH, int EPI>
+// NCO = output channels: NCH, or 3 for a gray image written as RGB (the reference widens gray input to RGB unless asked
+// for grayscale, src/imagew-main.c:1676-1684: three intermediate channels reading the same input channel, so one
+// resampled value serves the three; they differ only in their random-dither draws)
+template <int S, int STEP, int NCH, int EPI, int NCO = NCH>
 __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
     iwb_h2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_u, const H2Params p) {
   constexpr int SS = (S + 1) & ~1;
@@ -476,7 +479,8 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
   static_assert(STEP == 0 || (GU * NCH) % 4 == 0, "a uniform stage must end on a 16-byte chunk");
   constexpr int RING = NST * STAGE > NSTU * STAGE_U ? NST * STAGE : NSTU * STAGE_U;
   constexpr int WARP_BYTES = (RING + 32 * IWB2_OST_PITCH + 8 * 8 + 127) & ~127;
-  constexpr int FU = ((IWB2_OST_PITCH - 4) / NCH) & ~3;         // pixels per flush (multiple of 4; FU * NCH bytes fit a staging row)
+  static_assert(NCO == NCH || (NCH == 1 && NCO == 3), "output channels");
+  constexpr int FU = ((IWB2_OST_PITCH - 4) / NCO) & ~3;         // pixels per flush (multiple of 4; FU * NCO bytes fit a staging row)
   static_assert(KP >= 2 && NST >= 3 && GU >= 2 && NSTU >= 2, "pipeline depth");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -484,7 +488,7 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
   bool uni;
   s2_decode_part(p.part, blockIdx.x, 0, p.out_w, &xo0, &xo1, &uni);
   if (STEP == 0) uni = false;
-  const int ntab = p.same_tables ? 1 : NCH;
+  const int ntab = p.same_tables ? 1 : NCO;
 
   unsigned char *wbase = smem_raw + (size_t)warp * WARP_BYTES;
   unsigned char *ost = wbase + RING;                            // [32 rows][pitch]
@@ -575,9 +579,9 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
     for (int c = 0; c < NCH; c++) { acc[s][c] = 0.0; prod[s][c] = 0.0; }
 
   // random dither: this thread's draws are consecutive along its row, one per output pixel and channel
-  uint64_t rng[NCH];
+  uint64_t rng[NCO];
 #pragma unroll
-  for (int c = 0; c < NCH; c++) {
+  for (int c = 0; c < NCO; c++) {
     rng[c] = 0;
     if (EPI == 4 && y < p.row_hi) {
       uint64_t t = p.ch[c].prng_t1;
@@ -587,11 +591,11 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
     }
   }
   const unsigned ord_a = s2_addr(ord_s) + (y & 7) * 32;         // this row's eight ordered-dither thresholds
-  unsigned tab_c[NCH];                                          // per channel: table blob address, margin, top level
-  float qmargin[NCH];
-  int qtop[NCH];
+  unsigned tab_c[NCO];                                          // per output channel: table blob address, margin, top level
+  float qmargin[NCO];
+  int qtop[NCO];
 #pragma unroll
-  for (int c = 0; c < NCH; c++) {
+  for (int c = 0; c < NCO; c++) {
     const int tb = p.same_tables ? 0 : c;
     tab_c[c] = s2_addr(tab_s) + tb * IWB2_TAB_BYTES;
     qmargin[c] = p.q[tb].margin;
@@ -623,8 +627,8 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
   const unsigned ost_a = s2_addr(ost) + lane * IWB2_OST_PITCH;
   const bool walign = (((uintptr_t)p.out.pix | p.out.bpr) & 3) == 0;
   auto flush = [&](int upto) {
-    h2_flush(ost, p.out.pix + (size_t)(jb - p.out.row_origin) * p.out.bpr + (size_t)staged_from * NCH, p.out.bpr,
-             (upto - staged_from) * NCH, min(32, p.row_hi - jb), walign, lane);
+    h2_flush(ost, p.out.pix + (size_t)(jb - p.out.row_origin) * p.out.bpr + (size_t)staged_from * NCO, p.out.bpr,
+             (upto - staged_from) * NCO, min(32, p.row_hi - jb), walign, lane);
     staged_from = upto;
   };
   // slot k is complete: add its pending products, quantise + dither, stage the bytes, restart the slot
@@ -633,13 +637,18 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
     for (int c = 0; c < NCH; c++) if (DEFER) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
     if (xo >= xo0 && xo < xo1) {
       if (xo - staged_from >= FU) flush(xo);
-      const unsigned dstb = ost_a + (xo - staged_from) * NCH;
-      float t[NCH];
-      uint32_t draw[NCH];
-      int code[NCH], qg[NCH];
-      bool sure[NCH], all_sure = true;
+      const unsigned dstb = ost_a + (xo - staged_from) * NCO;
+      float t[NCO];
+      uint32_t draw[NCO];
+      int code[NCO], qg[NCO];
+      bool sure[NCO], all_sure = true;
 #pragma unroll
-      for (int c = 0; c < NCH; c++) {
+      for (int c = 0; c < NCO; c++) {
+        const int ci = NCO == NCH ? c : 0;                       // the intermediate channel behind output channel c
+        if (NCO != NCH && EPI != 4 && c > 0) {                   // same sample, same threshold: same code
+          t[c] = t[0]; draw[c] = 0; code[c] = code[0]; sure[c] = sure[0]; qg[c] = qg[0];
+          continue;
+        }
         t[c] = EPI == 3 ? s2_ldsf(ord_a + 4 * (xo & 7)) : 0.5f;
         draw[c] = 0;
         if (EPI == 4) {
@@ -647,21 +656,23 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
           rng[c] = iwb_prng_step(rng[c]);
           t[c] = (float)draw[c] * (1.0f / 4294967295.0f);
         }
-        code[c] = quantise8_try<EPI>(tab_c[c], qmargin[c], qtop[c], t[c], acc[k][c], &sure[c], &qg[c]);
+        code[c] = quantise8_try<EPI>(tab_c[c], qmargin[c], qtop[c], t[c], acc[k][ci], &sure[c], &qg[c]);
         all_sure = all_sure && sure[c];
       }
       if (__any_sync(0xffffffffu, !all_sure)) {                 // a few 1e-4 of the samples: exact FP64 decision
 #pragma unroll
-        for (int c = 0; c < NCH; c++) {
+        for (int c = 0; c < NCO; c++) {
+          const int ci = NCO == NCH ? c : 0;
+          if (NCO != NCH && EPI != 4 && c > 0) { code[c] = code[0]; continue; }
           if (!sure[c]) {
             const int tb = p.same_tables ? 0 : c;
             code[c] = exact8_v2<EPI == 1 ? 0 : (EPI == 2 ? 4 : (EPI == 3 ? 1 : 3))>((const double *)(tab_s + (size_t)tb * IWB2_TAB_BYTES + IWB2_TAB_THR),
-                                                                 p.q[tb].top, acc[k][c], qg[c], t[c], draw[c]);
+                                                                 p.q[tb].top, acc[k][ci], qg[c], t[c], draw[c]);
           }
         }
       }
 #pragma unroll
-      for (int c = 0; c < NCH; c++) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dstb + c), "r"(code[c]) : "memory");
+      for (int c = 0; c < NCO; c++) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dstb + c), "r"(code[c]) : "memory");
     }
 #pragma unroll
     for (int c = 0; c < NCH; c++) acc[k][c] = 0.0;

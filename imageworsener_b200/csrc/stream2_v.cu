@@ -4,8 +4,9 @@
 
 bool iwb2_tensor_maps_available() { return iwb2_tensor_map_encoder() != nullptr; }
 
-bool iwb2_supported(int SV, int SH, int nch, int epi) {
-  return iwb2_s_built(SV) && iwb2_s_built(SH) && (nch == 1 || nch == 3) && (epi == 1 || epi == 2 || epi == 3 || epi == 4);
+bool iwb2_supported(int SV, int SH, int nch, int nco, int epi) {
+  return iwb2_s_built(SV) && iwb2_s_built(SH) && (nch == 1 || nch == 3) && (nco == nch || (nch == 1 && nco == 3)) &&
+         (epi == 1 || epi == 2 || epi == 3 || epi == 4);
 }
 
 bool iwb2_run_v(const V2Job &job, cudaStream_t st) { return job.p.depth16 ? iwb2_run_v16(job, st) : iwb2_run_v8(job, st); }

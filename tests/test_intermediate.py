@@ -32,6 +32,7 @@ CASES = [
     ("down5_mitchell_holes_gray16", 640, 400, GRAY, 16, 128, 80, "-filter mitchell -grayscale", {}),
     ("up2_lanczos_s12", 200, 120, RGB, 8, 400, 240, "-filter lanczos -dither o", {}),
     ("up4_mitchell_s16_gray16", 100, 80, GRAY, 16, 400, 320, "-filter mitchell -grayscale -dither r", {}),
+    ("gray_as_rgb", 512, 384, GRAY, 8, 256, 192, "-filter lanczos -dither r", {}),
 ]
 
 

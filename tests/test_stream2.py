@@ -48,6 +48,12 @@ SHAPES = [
     ("up4_mitchell_s16", 160, 120, RGB, 640, 480, "-filter mitchell"),
     ("up2p4_lanczos_s16_gray", 200, 160, GRAY, 480, 384, "-filter lanczos -grayscale -dither halftone"),
     ("up4_down2_mixed", 160, 800, RGB, 640, 400, "-filter mitchell -dither o"),          # 16 windows across, 4 down
+    # gray input written as RGB (no -grayscale): one intermediate plane, three output bytes
+    ("gray_as_rgb_o", 1024, 512, GRAY, 512, 256, "-filter lanczos -dither o"),
+    ("gray_as_rgb_r", 1024, 512, GRAY, 512, 256, "-filter catrom -dither r"),                # three different draw sequences
+    ("gray_as_rgb_r2", 1000, 500, GRAY, 333, 250, "-filter catrom -dither r2"),              # same pattern on the three
+    ("gray_as_rgb_none_odd", 1000, 500, GRAY, 617, 333, "-filter lanczos2"),
+    ("gray_as_rgb_up_s12", 200, 160, GRAY, 400, 320, "-filter lanczos -dither halftone"),
 ]
 
 
@@ -172,6 +178,8 @@ SHAPES16 = [
     ("rgb16_down3_lanczos2", 1536, 480, RGB, 512, 160, "-filter lanczos2 -dither r"),
     ("rgb16_up2_lanczos_s12", 320, 200, RGB, 640, 400, "-filter lanczos -dither o"),
     ("gray16_up4_mitchell_s16", 160, 120, GRAY, 640, 480, "-filter mitchell -grayscale -dither r"),
+    ("gray16_as_rgb_r", 1024, 512, GRAY, 512, 256, "-filter catrom -dither r"),
+    ("gray16_as_rgb_o", 640, 400, GRAY, 320, 200, "-filter lanczos -dither o"),
 ]
 
 
@@ -209,7 +217,7 @@ def test_fast_path_unaligned_host_rows(prod, ref, opts, depth):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [s for s in SHAPES if "holes" in s[0] or "_s1" in s[0]], ids=lambda s: s[0])
+@pytest.mark.parametrize("shape", [s for s in SHAPES if "holes" in s[0] or "_s1" in s[0] or "gray_as_rgb" in s[0]], ids=lambda s: s[0])
 def test_windows_with_holes_take_the_streaming_kernels(prod, shape):
     """Jobs whose tap lists skip zero-weight samples, and enlargements with up to 16 open windows, are planned onto
     the generation-2 kernels, not the older ones."""
