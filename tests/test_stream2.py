@@ -133,10 +133,26 @@ def _near_integer_case(seed):
     return configs.Config(f"near{seed}", iw, ih, typ, 8, ow, oh, f"-width {ow} -height {oh} -filter {flt} {dither}{blur}")
 
 
+def _enlargement_case(seed):
+    """Enlargements at or next to 1.5x .. 4x per axis (independently; one axis may shrink): 12 and 16 open windows,
+    end taps dropped as exact zeros, gray input written as RGB, rows padded to 16 bytes."""
+    rng = np.random.default_rng(seed)
+    typ = RGB if rng.random() < 0.6 else GRAY
+    flt = rng.choice(["lanczos", "lanczos2", "catrom", "mitchell", "hermite", "triangle", "quadratic", "gaussian", "bspline", "mix"])
+    dither = rng.choice(["", "-dither o", "-dither halftone", "-dither r", "-dither r2"])
+    fx, fy = rng.choice([1.5, 2, 2.5, 3, 4, 0.5], 2)
+    iw, ih = int(rng.integers(40, 160)), int(rng.integers(24, 90))
+    ow = max(8, int(round(iw * fx)) + int(rng.integers(-3, 4)))
+    oh = max(8, int(round(ih * fy)) + int(rng.integers(-3, 4)))
+    gray = " -grayscale" if typ == GRAY and rng.random() < 0.5 else ""
+    return configs.Config(f"up{seed}", iw, ih, typ, 8, ow, oh, f"-width {ow} -height {oh} -filter {flt}{gray} {dither}")
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("gen", [_near_integer_case, _enlargement_case], ids=["reduce", "enlarge"])
 @pytest.mark.parametrize("seed", range(80))
-def test_fast_path_near_integer_factors_match_reference(prod, ref, seed):
-    cfg = _near_integer_case(seed)
+def test_fast_path_near_integer_factors_match_reference(prod, ref, seed, gen):
+    cfg = gen(seed)
     nch = L.imgtype_num_channels(cfg.imgtype)
     tight = configs.synth_rows(prod, cfg, seed=0x1234 + seed)
     bpr = (cfg.in_w * nch + 15) // 16 * 16

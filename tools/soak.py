@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from imageworsener_b200 import configs, libimagew as L  # noqa: E402
-from test_stream2 import _near_integer_case  # noqa: E402
+from test_stream2 import _enlargement_case, _near_integer_case  # noqa: E402
 
 
 def main():
@@ -37,6 +37,24 @@ def main():
                 bad += 1
                 print(f"DIFF seed {seed} {opts} {cfg.args!r} {cfg.in_w}x{cfg.in_h}: {nd} bytes", flush=True)
     print(f"random near-integer geometries: {n} cases x 3 variants, {samples} output bytes compared, {bad} cases differ, {time.time() - t0:.0f} s", flush=True)
+    badu = samplesu = 0
+    for seed in range(7000, 7000 + n):
+        cfg = _enlargement_case(seed)
+        nch = L.imgtype_num_channels(cfg.imgtype)
+        tight = configs.synth_rows(prod, cfg, seed=0x555 + seed)
+        bpr = (cfg.in_w * nch + 15) // 16 * 16
+        rows = np.full((cfg.in_h, bpr), 0x5A, np.uint8)
+        rows[:, : cfg.in_w * nch] = tight
+        _, b = configs.run_host(ref, cfg, tight)
+        for opts in ({}, {"cuda:gen": 1}):
+            _, a = configs.run_host(prod, cfg, rows, options=opts)
+            nd = int(np.count_nonzero(a != b))
+            samplesu += a.size
+            if nd:
+                badu += 1
+                print(f"DIFFUP seed {seed} {opts} {cfg.args!r} {cfg.in_w}x{cfg.in_h}: {nd} bytes", flush=True)
+    print(f"random enlargements (12 / 16 open windows, gray as RGB): {n} cases x 2 variants, {samplesu} output bytes compared, {badu} cases differ", flush=True)
+    bad += badu
     # the same geometries with 16-bit big-endian input (rows of 16-bit samples padded to 16 bytes)
     bad16 = samples16 = 0
     for seed in range(9000, 9000 + n // 2):
@@ -61,7 +79,8 @@ def main():
     big = 0
     for dither in ("-dither o", "-dither r", "", "-dither halftone"):
         for flt, ow, oh in (("lanczos", 3840, 2160), ("catrom", 2560, 1440), ("mitchell", 3833, 2160)):
-            cfg = configs.Config("big", 7680, 4320, L.IW_IMGTYPE_RGB, 8, ow, oh, f"-width {ow} -height {oh} -filter {flt} {dither}")
+            cfg = configs.Config("big", 7680, 4320, L.IW_IMGTYPE_RGB if flt != "mitchell" else L.IW_IMGTYPE_GRAY, 8, ow, oh,
+                                 f"-width {ow} -height {oh} -filter {flt} {dither}")
             rows = configs.synth_rows(prod, cfg, seed=0xABCDEF + ow)
             _, a = configs.run_host(prod, cfg, rows)
             _, b = configs.run_host(ref, cfg, rows)
