@@ -216,6 +216,7 @@ struct iwb200_job {
   int errdiff_next_row = 0;
   // where the FP32 intermediate of the last chunk lives (iwb200_job_read_intermediate)
   int last_path = -1, last_c0 = 0, last_c1 = 0, last_sh = 0;
+  int x0_override = -1;             // set by run_host while its device copy holds only the cropped columns
   size_t last_pitch = 0;
   const float *last_inter = nullptr;
   // optional per-kernel event timing
@@ -1343,6 +1344,7 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
 #endif
   DevInput in = job->in;
   in.pix = (const uint8_t *)d_in; in.bpr = in_bpr; in.row_origin = in_row_origin;
+  if (job->x0_override >= 0) in.x0 = job->x0_override;
   DevOutput out = job->out;
   out.pix = (uint8_t *)d_out; out.bpr = out_bpr; out.row_origin = r0;
 
@@ -1511,8 +1513,19 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
   // The device copy of the input gets a row pitch that is a multiple of 16 bytes (the TMA kernels need aligned rows);
   // the pitch conversion costs nothing: it is done by the copy engine (2-D H2D copy).
   size_t d_bpr = in_bpr;
+  size_t col_off = 0, row_bytes = in_bpr;      // the part of each host row that travels
 #if !defined(IWB_EMU)
-  if (job->fused.enabled && job->fused.v2 && in_bpr % 16 != 0 && !iwb_option(job->ctx, "cuda:keep_pitch")) d_bpr = (in_bpr + 15) & ~(size_t)15;
+  if (job->fused.enabled && job->fused.v2 && !iwb_option(job->ctx, "cuda:keep_pitch")) {
+    // a crop in x: only the cropped columns are copied, and they start an aligned device row (otherwise an odd crop
+    // origin would rule the TMA kernels out, and the columns outside the crop would cross PCIe for nothing)
+    const size_t bpp = (size_t)job->in.nch_phys * (job->in.depth / 8);
+    if (job->in.orient == 0 && job->in.x0 > 0 && !job->in.is_float && (job->in.depth == 8 || job->in.depth == 16)) {
+      col_off = (size_t)job->in.x0 * bpp;
+      row_bytes = (size_t)job->in_w * bpp;
+      d_bpr = row_bytes;
+    }
+    if (d_bpr % 16 != 0) d_bpr = (d_bpr + 15) & ~(size_t)15;
+  }
 #endif
   const size_t in_bytes = (size_t)(last - first + 1) * d_bpr;
   const size_t out_bytes = (size_t)(r1 - r0) * out_bpr;
@@ -1521,7 +1534,7 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
   if (!job->d_in || !job->d_out) { job->d_in_bytes = job->d_out_bytes = 0; return 0; }
   iwb_timings &tm = job->ctx->timings;
 #if defined(IWB_EMU)
-  (void)tm;
+  (void)tm; (void)col_off; (void)row_bytes;
   if (!dev_h2d(job->d_in, (const uint8_t *)h_in + (size_t)first * in_bpr, in_bytes, 0, job->err)) return 0;
   if (!iwb200_job_run_device(job, job->d_in, in_bpr, first, job->d_out, out_bpr, r0, r1, 0)) return 0;
   if (!dev_d2h(h_out, job->d_out, out_bytes, 0, job->err)) return 0;
@@ -1575,11 +1588,11 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
     if (nsub == 1 || k == nsub - 1) l = last;
     if (l > copied_to) {
       const size_t off = (size_t)(copied_to + 1 - first) * d_bpr, n = (size_t)(l - copied_to) * in_bpr;
-      if (d_bpr == in_bpr) {
+      if (d_bpr == in_bpr && col_off == 0) {
         ok = dev_h2d((uint8_t *)job->d_in + off, (const uint8_t *)h_in + (size_t)(copied_to + 1) * in_bpr, n, s_in, job->err);
       } else {
-        ok = cudaMemcpy2DAsync((uint8_t *)job->d_in + off, d_bpr, (const uint8_t *)h_in + (size_t)(copied_to + 1) * in_bpr, in_bpr, in_bpr,
-                               (size_t)(l - copied_to), cudaMemcpyHostToDevice, s_in) == cudaSuccess;
+        ok = cudaMemcpy2DAsync((uint8_t *)job->d_in + off, d_bpr, (const uint8_t *)h_in + (size_t)(copied_to + 1) * in_bpr + col_off, in_bpr,
+                               row_bytes, (size_t)(l - copied_to), cudaMemcpyHostToDevice, s_in) == cudaSuccess;
         if (!ok) job->err = "H2D copy (2-D) failed";
       }
       copied_to = l;
@@ -1590,8 +1603,10 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
     int b0, b1;
     bounds(k, &b0, &b1);
     cudaStreamWaitEvent(s_k, ev(2 * k), 0);
+    job->x0_override = col_off ? 0 : -1;
     ok = ok && iwb200_job_run_device(job, job->d_in, d_bpr, first, (uint8_t *)job->d_out + (size_t)(b0 - r0) * out_bpr, out_bpr,
                                      b0, b1, s_k);
+    job->x0_override = -1;
     cudaEventRecord(ev(2 * k + 1), s_k);
     cudaStreamWaitEvent(s_out, ev(2 * k + 1), 0);
     ok = ok && dev_d2h((uint8_t *)h_out + (size_t)(b0 - r0) * out_bpr, (uint8_t *)job->d_out + (size_t)(b0 - r0) * out_bpr,

@@ -15,8 +15,9 @@
  *     "cuda:fused" (0: generic per-sample kernels only), "cuda:strip2" / "cuda:seg2" (rows / pixels per CTA part of
  *     the generation-2 kernels), "cuda:strip" / "cuda:seg" / "cuda:nc" (generation 1), "cuda:chunk_mb" (size of the
  *     FP32 intermediate), "cuda:pipeline" (sub-bands of the host-buffer pipeline), "cuda:overlap" (two-stream V/H
- *     overlap, off), "cuda:keep_pitch" (1: the device copy of a host image keeps the caller's row stride even when it
- *     is not a multiple of 16 bytes, which rules the TMA kernels out; default is a 16-byte aligned device pitch);
+ *     overlap, off), "cuda:keep_pitch" (1: the device copy of a host image keeps the caller's row stride and whole rows;
+ *     default: a 16-byte aligned device pitch, and with a crop in x only the cropped columns are copied, so that
+ *     the TMA kernels apply whatever the stride and crop origin are);
  *   - iwb200_job_*: the plan/launch layer under iw_process_image() for callers that keep images resident
  *     in HBM (benchmarks, multi-GPU band sharding).
  */

@@ -171,14 +171,20 @@ def test_fast_path_near_integer_factors_match_reference(prod, ref, seed, gen):
     ("-filter catrom -dither r", {"cuda:chunk_mb": 1}),           # ... with absolute PRNG coordinates
     ("-filter lanczos -dither o -negate", {}),                    # post kernel behind the horizontal pass
     ("-filter lanczos -dither o -crop 32,10,800,500", {}),        # crop origin on a 16-byte boundary (TMA kernels)
-    ("-filter lanczos -dither o -crop 33,11,801,499", {}),        # ... and off it (generation-1 kernels)
+    ("-filter lanczos -dither o -crop 33,11,801,499", {}),        # ... and off it: the host copy re-bases the crop on an aligned row
+    ("-filter lanczos -dither o -crop 33,11,801,499", {"cuda:keep_pitch": 1}),   # ... or not (generation-1 kernels)
     ("-filter mitchell -crop 64,0,640,768", {"cuda:chunk_mb": 1}),
-], ids=["chunks", "chunks-random", "negate", "crop-aligned", "crop-unaligned", "crop-chunks"])
-def test_fast_path_chunks_negate_crop(prod, ref, extra, opts):
+    ("-filter catrom -dither r -crop 5,3,1000,700", {"cuda:band": "1/3"}),       # a band of a cropped image
+], ids=["chunks", "chunks-random", "negate", "crop-aligned", "crop-unaligned", "crop-unaligned-gen1", "crop-chunks", "crop-band"])
+@pytest.mark.parametrize("depth", [8, 16])
+def test_fast_path_chunks_negate_crop(prod, ref, extra, opts, depth):
     ow, oh = (512, 384) if "-crop" not in extra else (400, 250)
-    cfg = configs.Config("misc", 1024, 768, RGB, 8, ow, oh, f"-width {ow} -height {oh} {extra}")
+    cfg = configs.Config("misc", 1024, 768, RGB, depth, ow, oh, f"-width {ow} -height {oh} {extra}")
     rows = configs.synth_rows(prod, cfg)
-    _, a = configs.run_host(prod, cfg, rows, options=opts)
+    if "cuda:band" in opts:                                      # all three bands, concatenated
+        a = np.concatenate([configs.run_host(prod, cfg, rows, options={"cuda:band": f"{i}/3"})[1] for i in range(3)], axis=0)
+    else:
+        _, a = configs.run_host(prod, cfg, rows, options=opts)
     _, b = configs.run_host(ref, cfg, rows)
     nd = int(np.count_nonzero(a != b))
     assert nd == 0, f"{nd} differing bytes of {a.size}"
