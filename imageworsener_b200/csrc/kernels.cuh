@@ -103,8 +103,8 @@ struct DevChanOut {       // what happens to a resampled intermediate channel
   const double *nc_tbl;   // [255]
   int ntab;               // entries in thr/codeval/linval
   const double *thr;      // linear-space lower bound of level q
-  const double *codeval;  // stored code of level q
-  const double *linval;   // linear value of that code
+  const double *codeval;  // stored code of level q; NULL: the code is q itself (every table that is not posterised)
+  const double *linval;   // linear value of that code (the same array as thr when the code is q itself)
   double maxcode;
   int color_count;
   int guess_cs;           // colour space of the table levels (IW_CSTYPE_*), -1: no closed form (plain binary search)
@@ -289,12 +289,16 @@ IWB_HD Candidates candidates_linear(const DevChanOut &o, double s) {
 }
 
 // Non-linear target space: level q is the largest one whose linear lower bound thr[q] is <= s.
+// (identity tables carry no code array: two gathers fewer per sample, and linval aliases thr, so the bounds the
+// search has just read are the candidates' linear values)
+IWB_HD double code_of_level(const DevChanOut &o, int q) { return o.codeval ? o.codeval[q] : (double)q; }
+
 IWB_HD Candidates candidates_table(const DevChanOut &o, double s) {
   Candidates c;
   const int top = o.ntab - 1;
   if (s > 0.999999999) {
     c.exact = 1;
-    c.code_lo = c.code_hi = o.codeval[top];
+    c.code_lo = c.code_hi = code_of_level(o, top);
     c.lin_lo = c.lin_hi = o.linval[top];
     return c;
   }
@@ -326,13 +330,13 @@ IWB_HD Candidates candidates_table(const DevChanOut &o, double s) {
   if (lo != top && o.thr[top] <= s) lo = top;
   if (lo >= top) {
     c.exact = 1;
-    c.code_lo = c.code_hi = o.codeval[top];
+    c.code_lo = c.code_hi = code_of_level(o, top);
     c.lin_lo = c.lin_hi = o.linval[top];
     return c;
   }
   c.exact = 0;
-  c.code_lo = o.codeval[lo];
-  c.code_hi = o.codeval[lo + 1];
+  c.code_lo = code_of_level(o, lo);
+  c.code_hi = code_of_level(o, lo + 1);
   c.lin_lo = o.linval[lo];
   c.lin_hi = o.linval[lo + 1];
   return c;

@@ -374,10 +374,16 @@ bool build_output_tables(iwb200_job *job, const iw_context *ctx, const iwb_out_c
   o->guess_gamma = (cs.cstype == IW_CSTYPE_GAMMA && cs.gamma > 0.0) ? (float)(1.0 / cs.gamma) : 1.0f;
   job->thr_host[job->building_channel] = thr;
   o->thr = job->upload(thr.data(), thr.size());
-  o->codeval = job->upload(code.data(), code.size());
-  o->linval = job->upload(lin.data(), lin.size());
+  if (oc.color_count == 0) {                                     // code q is level q and its linear value is the level's bound
+    o->codeval = nullptr;
+    o->linval = o->thr;
+  } else {
+    o->codeval = job->upload(code.data(), code.size());
+    o->linval = job->upload(lin.data(), lin.size());
+    if (!o->codeval) return false;
+  }
   (void)ctx;
-  return o->thr && o->codeval && o->linval;
+  return o->thr && o->linval;
 }
 
 }  // namespace
