@@ -1030,6 +1030,27 @@ static bool pool_enabled() {
 
 extern "C" {
 
+int iwb200_debug_build_schedule(const int *tap_first, const int *tap_src, const double *tap_w, int n_in, int n_out,
+                                int *slots, int *first, int *last, double *w) {
+#if defined(IWB_EMU)
+  (void)tap_first; (void)tap_src; (void)tap_w; (void)n_in; (void)n_out; (void)slots; (void)first; (void)last; (void)w;
+  return 0;
+#else
+  if (!tap_first || !tap_src || !tap_w || n_out < 1 || n_in < 1) return 0;
+  iwb_axis_table t;
+  t.mode = 0; t.n_in = n_in; t.n_out = n_out;
+  t.first.assign(tap_first, tap_first + n_out + 1);
+  t.src.assign(tap_src, tap_src + tap_first[n_out]);
+  t.w.assign(tap_w, tap_w + tap_first[n_out]);
+  HostSched hs;
+  if (!build_sched(t, 16, &hs)) return 0;
+  if (slots) *slots = hs.S;
+  for (int o = 0; o < n_out; o++) { if (first) first[o] = hs.first[o]; if (last) last[o] = hs.last[o]; }
+  if (w) std::copy(hs.w.begin(), hs.w.end(), w);
+  return 1;
+#endif
+}
+
 const char *iwb200_version(void) {
 #if defined(IWB_EMU)
   return "imagew_b200 0.1 host-emulation (test build, not the product)";

@@ -348,6 +348,13 @@ void iwb200_job_reset_stats(iwb200_job *job);
 int iwb200_debug_plan_parts(const int *first, const int *last, int n_out, int lo, int hi, int base, int align, int S, int want,
                             int len_override, int g_min, int step_wanted, int *out);
 
+/* Test hook: turn a tap list (tap_first[n_out+1] offsets into tap_src / tap_w, as the weight-list builder emits them)
+ * into the streaming schedule of the fast path; pure host code.  Returns 0 if the list does not qualify, else 1 with
+ * *slots = accumulator slots S, first/last[n_out] = the (possibly widened) windows and w[n_in * S] = the weight of
+ * input r for slot s at w[r * S + s] (w may be NULL). */
+int iwb200_debug_build_schedule(const int *tap_first, const int *tap_src, const double *tap_w, int n_in, int n_out,
+                                int *slots, int *first, int *last, double *w);
+
 /* Deterministic synthetic input and output fingerprint used by the benchmarks and the full-size parity tests
  * (SURVEY.md section 8c): xorshift64 noise (s^=s<<13; s^=s>>7; s^=s<<17; byte = s>>24), FNV-1a 64-bit. */
 void iwb200_synth_xorshift(uint8_t *buf, size_t n, uint64_t seed);

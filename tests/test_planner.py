@@ -144,3 +144,89 @@ def test_first_outputs_after_a_break_in_the_progression_are_not_uniform(plan):
             for q in range(a, b):
                 assert last2[q] == p["u_ref_last"] + step * (q - p["u_ref_o"])
                 assert q - S < 0 or last2[q - S] <= last2[q] - GU
+
+
+# ---- streaming schedules from tap lists (pipeline.cu:build_sched) ---------------------------------------------
+
+def _schedule(dll, lists, n_in):
+    """lists[o] = [(src, weight), ...] in list order."""
+    fn = dll.iwb200_debug_build_schedule
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 4
+    n_out = len(lists)
+    tf = np.zeros(n_out + 1, np.int32)
+    for o, l in enumerate(lists):
+        tf[o + 1] = tf[o] + len(l)
+    src = np.array([s for l in lists for s, _ in l], np.int32)
+    wt = np.array([w for l in lists for _, w in l], np.float64)
+    S = C.c_int()
+    first, last = np.zeros(n_out, np.int32), np.zeros(n_out, np.int32)
+    w = np.full(n_in * 16, np.nan)
+    ok = fn(tf.ctypes.data, src.ctypes.data, wt.ctypes.data, n_in, n_out, C.byref(S), first.ctypes.data, last.ctypes.data, w.ctypes.data)
+    if not ok:
+        return None
+    return S.value, first, last, w[: n_in * S.value].reshape(n_in, S.value)
+
+
+@pytest.fixture(scope="module")
+def dll():
+    return L.load_product().dll
+
+
+def _check_schedule(lists, n_in, res):
+    """Every tap's weight sits at (its source, its output's slot); everything else the slot sees while the window is
+    open is exactly +0.0; windows cover their taps and are monotone; no two open windows share a slot."""
+    S, first, last, w = res
+    expect = np.zeros_like(w)
+    for o, l in enumerate(lists):
+        assert first[o] <= min(s for s, _ in l) and last[o] >= max(s for s, _ in l)
+        for s, wt in l:
+            expect[s, o % S] = wt
+    assert np.array_equal(w, expect) and not np.signbit(w[w == 0]).any()
+    assert (np.diff(first) >= 0).all() and (np.diff(last) >= 0).all()
+    for o in range(S, len(lists)):
+        assert last[o - S] < first[o], "slot reused while its previous window is still open"
+
+
+def test_schedule_of_contiguous_windows(dll):
+    lists = [[(2 * o + k, 0.25) for k in range(4) if 0 <= 2 * o + k - 1 < 40] for o in range(20)]
+    lists = [[(s - 1, w) for s, w in l] for l in lists]
+    res = _schedule(dll, lists, 40)
+    assert res is not None and res[0] == 2
+    _check_schedule(lists, 40, res)
+
+
+def test_schedule_accepts_holes_inside_a_window(dll):
+    """3x reduction with a cubic filter: the tap at |x| = 1 has weight exactly 0 and is absent from the list."""
+    lists = []
+    for o in range(30):
+        c = 3 * o + 1
+        taps = [(s, 0.1 + 0.01 * k) for k, s in enumerate(range(c - 5, c + 6)) if 0 <= s < 90 and s not in (c - 3, c + 3)]
+        lists.append(taps)
+    res = _schedule(dll, lists, 90)
+    assert res is not None
+    _check_schedule(lists, 90, res)
+    S, first, last, w = res
+    assert w[3 * 10 + 1 + 3, 10 % S] == 0.0                  # the hole carries a zero weight
+
+
+def test_schedule_widens_windows_whose_end_tap_was_dropped(dll):
+    """Enlargement: an output whose first (last) tap was an exact zero starts after (ends before) its neighbour."""
+    lists = [[(0, .5), (1, .5)], [(1, 1.0)], [(0, .1), (1, .8), (2, .1)], [(1, .5), (2, .5)], [(1, .2), (2, .6), (3, .2)],
+             [(2, 1.0)], [(2, .5), (3, .5)], [(2, .1), (3, .9)]]
+    res = _schedule(dll, lists, 4)
+    assert res is not None
+    _check_schedule(lists, 4, res)
+    S, first, last, w = res
+    assert first[1] == 0 and last[5] == 3                      # widened to keep starts and ends monotone
+
+
+def test_schedule_rejects_what_the_streaming_kernels_cannot_do(dll):
+    ok = [[(o, 0.5), (o + 1, 0.5)] for o in range(10)]
+    assert _schedule(dll, ok, 11) is not None
+    assert _schedule(dll, [[(-1, 0.5), (0, 0.5)]] + ok[1:], 11) is None          # virtual sample (TRANSPARENT edge)
+    assert _schedule(dll, [[(0, 0.5), (0, 0.5)]] + ok[1:], 11) is None           # repeated sample (REPLICATE edge)
+    assert _schedule(dll, ok[:5] + [[]] + ok[6:], 11) is None                    # empty window
+    assert _schedule(dll, ok[:5] + [[(1, 1.0)]] + ok[6:], 11) is None            # window jumps back by more than a dropped tap
+    wide = [[(s, 1.0 / 40) for s in range(o, o + 40)] for o in range(30)]
+    assert _schedule(dll, wide, 70) is None                                      # more than 16 windows open at once
