@@ -61,3 +61,21 @@ def test_option_dictionary(emu):
     lib.iw_set_option(ctx, b"backend", b"cpu")
     assert lib.iw_get_option(ctx, b"backend") == b"cpu"
     lib.iw_destroy_context(ctx)
+
+
+def test_header_is_plain_c_and_a_c_caller_links(tmp_path):
+    """include/imagew_b200.h is the boundary for C callers (the reference is C): it must compile as C99 with
+    warnings on, and a plain C program using the public calls (tools/batch_driver.c) must link against the library."""
+    import subprocess
+    so = _build.build_product()
+    hdr_only = tmp_path / "hdr.c"
+    hdr_only.write_text('#include "imagew_b200.h"\nint main(void) { return IW_VERSION_INT == 0x010305 ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, "-c", str(hdr_only), "-o", str(tmp_path / "hdr.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = tmp_path / "batch_driver"
+    r = subprocess.run(["gcc", "-O1", "-pthread", "-Wall", "-I", inc, os.path.join(ROOT, "tools", "batch_driver.c"), "-o", str(exe),
+                        "-L", os.path.dirname(so), "-l:" + os.path.basename(so), "-Wl,-rpath," + os.path.dirname(so)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
