@@ -10,6 +10,8 @@ steps); `e2e` times the public C-ABI call iw_process_image() on HOST buffers, so
 input and the D2H copy of the result.  With N > 1 (launched by torchrun, one rank per GPU) every rank processes its
 own image (images shard across GPUs with no data-path collective: weak scaling); the time is the max over ranks.
 `--impl reference` times the unmodified reference build (oracle/_ref) on the host cores.
+`--config` also takes the other BASELINE.json configurations (cfg3, cfg4auto, cfg4box, cfg5) and a few everyday shapes
+(frac, catrom3, up2, up4, gray2: imageworsener_b200/configs.py); the driver's line is always cfg2.
 """
 from __future__ import annotations
 
