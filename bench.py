@@ -30,22 +30,43 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-from imageworsener_b200 import configs, libimagew as L  # noqa: E402
+from imageworsener_b200 import configs, libimagew as L  # noqa: E402  (the reference arm uses only the config
+#                                                                  # descriptions and the ctypes binding class from it)
 
 METRIC = "output Mpix/s, 8K->4K Lanczos3 linear-light RGB8 + ordered dither"
 KERNEL_CLASSES = ["v_pass_generic", "h_pass_epilogue", "prng_fill", "errdiff", "post", "v_pass_stream"]
-# measured FP64 issue rate for independent DMUL+DADD pairs (tools/fp64_peak.cu, profiles/r1_fp64_peak.txt)
+# measured FP64 issue rate for independent DMUL+DADD pairs.  MEASURED_PEAKS.json has no FP64 entry: this is the
+# builder's own microbenchmark (tools/fp64_peak.cu, profiles/r1_fp64_peak.txt), consistent with 148 SMs x 64 lanes x
+# 1.965 GHz = 18.6 T; the JSON line says so (`fp64.peak_source`)
 FP64_PEAK_LANE_INSTR = 18.4e12
+FP64_PEAK_SOURCE = "builder-measured (tools/fp64_peak.cu, profiles/r1_fp64_peak.txt); not in MEASURED_PEAKS.json"
+
+
+def kernel_sources_sha() -> str:
+    """Fingerprint of the device code the library was built from (the ncu capture in profiles/traffic.json is only
+    valid for the kernels it was taken on)."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "imageworsener_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".inc")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def ncu_traffic(kernel_class: str):
-    """DRAM bytes (read + write) per launch of the kernel class from the committed `ncu --set full` capture of
-    this same command (profiles/traffic.json, written by tools/ncu_summary.py); None if not recorded."""
+    """DRAM bytes (read + write) per launch of the kernel class from the committed `ncu --set full` capture of this
+    same command (profiles/traffic.json, written by tools/ncu_summary.py).  The capture is stamped with the
+    fingerprint of the kernel sources it was taken on; None (and why) when HEAD's kernels differ or nothing is recorded."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p)).get(kernel_class)
+        d = json.load(open(p))
     except Exception:  # noqa: BLE001
-        return None
+        return None, "no capture recorded"
+    if d.get("kernel_sources_sha") != kernel_sources_sha():
+        return None, f"capture is of other kernel sources ({d.get('kernel_sources_sha')}, commit {d.get('commit')})"
+    return d.get(kernel_class), f"ncu --set full capture, commit {d.get('commit')}"
 
 
 def env_int(name, default):
@@ -159,10 +180,21 @@ def make_ctx(lib: L.Lib, cfg, rows=None, options=None):
     return ctx
 
 
+def reference_lib():
+    import oracle                        # test infrastructure: the unmodified reference build (oracle/_ref)
+    return oracle.load_reference()
+
+
+def synth_rows_host(cfg, seed=configs.XORSHIFT_SEED):
+    """The synthetic input without the product library (oracle/libiworacle.so's plain-C generator)."""
+    import oracle
+    return oracle.synth_xorshift(cfg.in_bytes, seed).reshape(cfg.in_h, cfg.in_bpr)
+
+
 def cpu_reference_once(cfg, rows, threads: int):
     """`threads` reference contexts in parallel, one image each (the reference has no intra-image threading).
     Returns seconds."""
-    ref = L.load_reference()
+    ref = reference_lib()
     errs = []
 
     def work():
@@ -183,29 +215,40 @@ def cpu_reference_once(cfg, rows, threads: int):
     return dt
 
 
+def workload_config(name, cfg):
+    """The `config` keys both arms print (the driver compares them)."""
+    return {"workload": f"{name}: {cfg.description}", "in": [cfg.in_w, cfg.in_h], "out": [cfg.out_w, cfg.out_h]}
+
+
 def run_reference_arm(args, rank, world):
+    """The unmodified reference build on the host cores, on the SAME configuration as the GPU arm (full size).  A step
+    = `threads` contexts in parallel, one whole image each (the reference cannot thread one image); nothing of the
+    product is loaded."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     threads = max(1, min(cores, 16))
-    total = args.steps + args.warmup
-    scale = 1 if total <= 4 else (2 if total <= 12 else 4)   # bound the run to a few minutes
-    cfg = configs.get(args.config, scale=scale)
-    helper = L.load_product()            # only the synthetic-input helper (plain host C) is used from it
-    rows = configs.synth_rows(helper, cfg)
-    for _ in range(args.warmup):
+    cfg = configs.get(args.config)
+    rows = synth_rows_host(cfg)
+    # bound the run: one 8K image is ~3.5 s on one core, so steps x that must stay within a few minutes
+    t_probe = cpu_reference_once(cfg, rows, threads) if args.warmup > 0 else None
+    budget_s = 420.0
+    steps = args.steps
+    if t_probe is not None and t_probe * (args.steps + max(0, args.warmup - 1)) > budget_s:
+        steps = max(1, int(budget_s / t_probe) - max(0, args.warmup - 1))
+    for _ in range(max(0, args.warmup - 1)):
         cpu_reference_once(cfg, rows, threads)
     t = 0.0
-    for _ in range(args.steps):
+    for _ in range(steps):
         t += cpu_reference_once(cfg, rows, threads)
-    value = threads * args.steps * cfg.out_mpix / t
-    sample = (f"{threads} reference contexts in parallel (one thread each), each resizing one "
-              f"{cfg.in_w}x{cfg.in_h} image (1/{scale} linear scale of the workload) per step")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps, "higher_is_better": True,
+    value = threads * steps * cfg.out_mpix / t
+    sample = (f"{threads} reference contexts in parallel (one thread each; the reference has no intra-image "
+              f"threading), each resizing one full {cfg.in_w}x{cfg.in_h} image per step; {steps} timed steps"
+              + ("" if steps == args.steps else f" (of {args.steps} asked: bounded to ~{budget_s:.0f} s)"))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * t / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.config}: {cfg.description}", "in": [cfg.in_w, cfg.in_h],
-                       "out": [cfg.out_w, cfg.out_h]},
+            "config": workload_config(args.config, cfg),
             "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -370,14 +413,15 @@ def main():
     taps = info.taps_v + info.taps_h
     step_gbs = alg_bytes_step / (ms_per_step * 1e-3) / 1e9
     fp64_rate = 2.0 * taps / (ms_per_step * 1e-3)
+    traffic, traffic_src = ncu_traffic(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_step": alg_bytes_step, "launches_per_step": lp,
                 "avg_launch_ms": avg_launch_ms, "kernel_ms_per_step": stats,
                 "whole_step": {"achieved": step_gbs, "frac": step_gbs / peak},
                 "fp64_tap_pairs_per_step": taps,
                 "fp64": {"achieved_lane_instr_per_s": fp64_rate, "peak_lane_instr_per_s": FP64_PEAK_LANE_INSTR,
-                         "frac": fp64_rate / FP64_PEAK_LANE_INSTR,
+                         "peak_source": FP64_PEAK_SOURCE, "frac": fp64_rate / FP64_PEAK_LANE_INSTR,
                          "hbm_frac_ceiling": (alg_bytes_step / peak / 1e9) / (2.0 * taps / FP64_PEAK_LANE_INSTR)},
                 "note": "every tap is one DMUL + one DADD (FMA forbidden by bit-exactness): the FP64 pipe binds before "
                         "HBM, `fp64.hbm_frac_ceiling` is the HBM fraction at 100 % FP64 issue; see DESIGN.md"}
@@ -413,7 +457,8 @@ def main():
 
     # ---------------- CPU baseline: the reference build on this box's host cores ------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(L.REFERENCE_SO):
+    import oracle                                                    # (the checker / CPU baseline; never timed as ours)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(oracle.REFERENCE_SO):
         dt = cpu_reference_once(cfg, rows, 1)
         cpu = {"value": cfg.out_mpix / dt, "unit": "Mpix/s", "cores": 1, "kind": "reference",
                "sample": f"one full {cfg.in_w}x{cfg.in_h} image through the unmodified reference build, 1 thread "
@@ -423,12 +468,11 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if band_mode else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"{args.config}: {cfg.description}", "in": [cfg.in_w, cfg.in_h],
-                           "out": [cfg.out_w, cfg.out_h], "images_per_step_per_gpu": 1,
+                "config": {**workload_config(args.config, cfg), "images_per_step_per_gpu": 1,
                            "sharding": ("one image split into output-row bands, gathered to rank 0 with NCCL" if band_mode else
                                         "one image per GPU, no data-path collective") if world > 1 else "single GPU",
                            "l2_defeat": f"{nbuf} rotating input/output buffer sets ({nbuf * (cfg.in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2)",
-                           "fused_kernel": bool(info.uses_fused_kernel), "host_numa_binding": numa},
+                           "kernel_generation": int(info.uses_fused_kernel), "host_numa_binding": numa},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)

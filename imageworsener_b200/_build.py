@@ -90,7 +90,8 @@ def build_product(force: bool = False, verbose_ptxas: bool = False, out: str | N
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, DEVICE_SOURCES + HOST_SOURCES))
     _run([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-shared",
-          "-Xlinker", "-Bsymbolic", "-o", target] + objs)
+          "-Xlinker", "-Bsymbolic", "-Xlinker", "--version-script=" + os.path.join(CSRC, "exports.map"),
+          "-o", target] + objs)
     with open(stamp, "w") as fh:
         fh.write(flavour)
     return target

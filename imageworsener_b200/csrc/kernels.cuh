@@ -73,7 +73,7 @@ struct DevInput {
   int width, height;      // LOGICAL size (after the orientation transform)
   int orient;             // 0..7
   int x0, y0;             // crop origin, logical
-  int depth;              // 1,2,4,8,16 (uint) or 32 (float)
+  int depth;              // 1,2,4,8,16 (uint), 32 (float) or 64 (float input linearised to doubles on the host)
   int nch_phys;
   int is_float;
 };
@@ -163,6 +163,8 @@ IWB_HD unsigned raw_code(const DevInput &in, int px, int py, int ch) {
 }
 
 IWB_HD double raw_float(const DevInput &in, int px, int py, int ch) {
+  if (in.depth == 64)   // linearised on the host (pipeline.cu: float_prepass): aligned doubles
+    return *reinterpret_cast<const double *>(in.pix + (size_t)(py - in.row_origin) * in.bpr + ((size_t)in.nch_phys * px + ch) * 8);
   const uint8_t *p = in.pix + (size_t)(py - in.row_origin) * in.bpr + ((size_t)in.nch_phys * px + ch) * 4;
   union { uint8_t b[4]; float f; } u;
   u.b[0] = p[0]; u.b[1] = p[1]; u.b[2] = p[2]; u.b[3] = p[3];

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "iwb_internal.h"
@@ -87,6 +88,24 @@ static void launch_serial(const P &p, int n, iwb_stream s) {  // n independent s
   iwb_block_per_item<Body, P><<<n, 32, 0, s>>>(p);
   g_launches++;
 }
+// The library switches to the job's device for the duration of a call and puts the caller's device back on return
+// (a multi-GPU application keeps its own current device).
+struct dev_guard {
+  int prev = -1;
+  explicit dev_guard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    if (device < 0 || prev == device) { prev = -1; return; }
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); prev = -1; }   // (reported by dev_select)
+  }
+  ~dev_guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+// true exactly once per (call site tag, device): per-device kernel attributes
+static bool first_on_device(std::atomic<unsigned long long> &mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  return !(mask.fetch_or(bit) & bit);
+}
 static bool dev_select(int device, std::string &err) {
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) {
@@ -111,6 +130,7 @@ static void launch(const P &p, size_t n, iwb_stream) { for (size_t i = 0; i < n;
 template <class Body, class P>
 static void launch_serial(const P &p, int n, iwb_stream) { for (int i = 0; i < n; i++) Body::run(p, (size_t)i); g_launches++; }
 static bool dev_select(int, std::string &) { return true; }
+struct dev_guard { explicit dev_guard(int) {} };
 #endif
 
 bool iwb_bkgd_is_translucent(const iw_context *ctx);  // plan.cpp
@@ -217,6 +237,8 @@ struct iwb200_job {
   // where the FP32 intermediate of the last chunk lives (iwb200_job_read_intermediate)
   int last_path = -1, last_c0 = 0, last_c1 = 0, last_sh = 0;
   int x0_override = -1;             // set by run_host while its device copy holds only the cropped columns
+  int float_prepass = 0;            // float input in a non-linear colourspace: run_host linearises it on the host first
+  int prepass_done = 0;             // (set by run_host around its run_device calls)
   size_t last_pitch = 0;
   const float *last_inter = nullptr;
   // optional per-kernel event timing
@@ -269,12 +291,32 @@ struct iwb200_job {
       std::vector<uint8_t>().swap(c.host);
       c.cap = c.used;  // closed
     }
+    s0_dirty = true;
     return true;
   }
   void *scratch(size_t bytes) {
     void *d = dev_alloc(bytes, err);
     if (d) allocs.push_back(d);
+    s0_dirty = true;
     return d;
+  }
+  // Tables are uploaded and scratch is allocated on the default stream (stream-ordered pool).  A caller's own
+  // non-blocking stream does not synchronise with it implicitly: before the first launch that follows such work the
+  // stream is ordered after it with an event (once per job and stream, not per call).
+  bool s0_dirty = true;
+  void *s0_event = nullptr, *s0_stream = nullptr;
+  void order_after_stream0(iwb_stream st) {
+#if !defined(IWB_EMU)
+    if (!st) return;                                            // the default stream itself
+    if (!s0_dirty && s0_stream == (void *)st) return;
+    if (!s0_event) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); s0_event = e; }
+    cudaEventRecord((cudaEvent_t)s0_event, 0);
+    cudaStreamWaitEvent((cudaStream_t)st, (cudaEvent_t)s0_event, 0);
+    s0_dirty = false;
+    s0_stream = (void *)st;
+#else
+    (void)st;
+#endif
   }
 };
 
@@ -474,19 +516,18 @@ template <int S, int NC>
 void launch_v(const VStreamParams &p, dim3 grid, size_t smem, iwb_stream st) {
   // the cp.async ring moves NC bytes per thread and row: needs NC in {4,8} and NC-byte aligned rows
   const bool ring = NC >= 4 && (p.bpr % NC == 0) && (((uintptr_t)p.src + p.x0_bytes) % NC == 0) && (p.ncols % NC == 0);
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<unsigned long long> attr{0};          // the attribute is per device
+  if (first_on_device(attr)) {
     cudaFuncSetAttribute(iwb_vstream<S, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(iwb_vstream<S, NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
   }
   if (ring) iwb_vstream<S, NC, true><<<grid, IWB_V_THREADS, smem, st>>>(p);
   else iwb_vstream<S, NC, false><<<grid, IWB_V_THREADS, smem, st>>>(p);
 }
 template <int S, int NCH, int R, int EPI>
 void launch_h(const HStreamParams &p, dim3 grid, size_t smem, iwb_stream st) {
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(iwb_hstream<S, NCH, R, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  static std::atomic<unsigned long long> attr{0};
+  if (first_on_device(attr)) cudaFuncSetAttribute(iwb_hstream<S, NCH, R, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   iwb_hstream<S, NCH, R, EPI><<<grid, IWB_H_THREADS, smem, st>>>(p);
 }
 
@@ -834,8 +875,10 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
     const size_t bytes = (size_t)(std::max(job->in_w * f->nch, f->ncols_pad) + 4) * f->pitch_j * sizeof(float);
     f->interT = (float *)job->scratch(bytes);
     if (!f->interT) return false;
+    job->order_after_stream0(stream);
     cudaMemsetAsync(f->interT, 0, bytes, stream);
   }
+  job->order_after_stream0(stream);
   const int nch = f->nch;
   // second-generation kernels: TMA needs 16-byte aligned rows
   const uint8_t *src0 = in.pix + (ptrdiff_t)(in.y0 - in.row_origin) * (ptrdiff_t)in.bpr + (size_t)in.x0 * nch * (f->depth16 ? 2 : 1);
@@ -848,6 +891,21 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
     if (nsub < 2 || rows_all < 64 * nsub || job->profiling) nsub = 1;
     const int half_rows = f->chunk_rows / 2;
     const size_t pitch = (size_t)f->ncols_pad + 4;
+    // sub-chunk boundaries: equal parts (multiples of 8 rows), each at most one buffer half / one chunk.  Decided
+    // before the streams are chosen: an overlapped run whose parts outgrow the event pool falls back to one stream
+    // (and whole-chunk parts) as a whole.
+    std::vector<int> cuts;
+    auto make_cuts = [&](int n) {
+      cuts.clear();
+      const int cap = n > 1 ? half_rows : f->chunk_rows;
+      const int parts = std::max(n, (rows_all + cap - 1) / cap);
+      int len = ((rows_all + parts - 1) / parts + 7) & ~7;
+      if (len > cap) len = std::max(8, cap & ~7);
+      for (int c = r0; c < r1; c += len) cuts.push_back(c);
+      cuts.push_back(r1);
+    };
+    make_cuts(nsub);
+    if (nsub > 1 && (int)cuts.size() - 1 > 64) { nsub = 1; make_cuts(1); }
     cudaStream_t sv = (cudaStream_t)stream, sh = sv;
     if (nsub > 1) {
       if (!f->aux_stream) { cudaStream_t t; cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking); f->aux_stream = t; }
@@ -855,18 +913,6 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
       sh = (cudaStream_t)f->aux_stream;
       cudaEventRecord((cudaEvent_t)f->ev[128], sv);             // everything queued before this call
       cudaStreamWaitEvent(sh, (cudaEvent_t)f->ev[128], 0);
-    }
-    // sub-chunk boundaries: equal parts (multiples of 8 rows), each at most one buffer half / one chunk
-    std::vector<int> cuts;
-    {
-      const int cap = nsub > 1 ? half_rows : f->chunk_rows;
-      int parts = std::max(nsub, (rows_all + cap - 1) / cap);
-      parts = std::min(parts, 64);
-      int len = ((rows_all + parts - 1) / parts + 7) & ~7;
-      if (len > cap) len = cap & ~7;
-      for (int c = r0; c < r1; c += len) cuts.push_back(c);
-      cuts.push_back(r1);
-      if ((int)cuts.size() - 1 > 64) nsub = 1;                  // (cannot happen for sane sizes; keeps the event pool bounded)
     }
     const int nparts = (int)cuts.size() - 1;
     for (int i = 0; i < nparts; i++) {
@@ -959,7 +1005,12 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
 
 static void job_free(iwb200_job *job) {
   if (!job) return;
+  dev_guard on_device(job->device);
 #if !defined(IWB_EMU)
+  // memory goes back to the stream-ordered pool on the default stream: nothing of this job may still be running on a
+  // caller's stream
+  if (job->used_external_stream) { cudaDeviceSynchronize(); job->used_external_stream = 0; }
+  if (job->s0_event) cudaEventDestroy((cudaEvent_t)job->s0_event);
   for (int k = 0; k < 3; k++) if (job->streams[k]) cudaStreamDestroy((cudaStream_t)job->streams[k]);
   for (void *e : job->events) cudaEventDestroy((cudaEvent_t)e);
   for (void *e : job->fused.ev) cudaEventDestroy((cudaEvent_t)e);
@@ -1065,7 +1116,7 @@ void iwb200_job_destroy(iwb200_job *job) {
   if (!job) return;
   if (pool_enabled() && job->err.empty() && !job->key.empty()) {
 #if !defined(IWB_EMU)
-    if (job->used_external_stream) { cudaSetDevice(job->device); cudaDeviceSynchronize(); job->used_external_stream = 0; }
+    if (job->used_external_stream) { dev_guard on_device(job->device); cudaDeviceSynchronize(); job->used_external_stream = 0; }
 #endif
     job->ctx = nullptr;
     iwb200_job *evict = nullptr;
@@ -1103,18 +1154,18 @@ static iwb200_job *job_build(iw_context *ctx, int device) {
     fail(job, "CUDA backend: unsupported input bit depth");
     return job;
   }
-  if (is_float_in && !ctx->no_gamma && ctx->img1cs.cstype != IW_CSTYPE_LINEAR) {
-    // a continuous pow() cannot be tabulated; evaluating it on the device would not be bit-exact
-    fail(job, "CUDA backend: floating-point input is supported only in a linear colorspace");
-    return job;
-  }
+  // Floating-point samples in a non-linear colourspace: the reference evaluates the transfer curve per sample with
+  // the host libm (src/imagew-main.c:53-66, :348-372).  A continuous pow() cannot be tabulated and the device's pow is
+  // not bit-identical, so iwb200_job_run_host converts such input to linear FP64 samples on the host cores, with the
+  // same libm, before the upload (float_prepass); the kernels then read doubles (DevInput::depth 64).
+  job->float_prepass = is_float_in && !ctx->no_gamma && ctx->img1cs.cstype != IW_CSTYPE_LINEAR;
 
   DevInput &in = job->in;
   in.pix = nullptr; in.bpr = ctx->img1.bpr; in.row_origin = 0;
   in.width = ctx->img1.width; in.height = ctx->img1.height;
   in.orient = (int)(ctx->img1.orient_transform & 7);
   in.x0 = ctx->in_x0; in.y0 = ctx->in_y0;
-  in.depth = ctx->img1.bit_depth; in.nch_phys = ctx->in_nch_phys; in.is_float = is_float_in;
+  in.depth = job->float_prepass ? 64 : ctx->img1.bit_depth; in.nch_phys = ctx->in_nch_phys; in.is_float = is_float_in;
 
   DevOutput &out = job->out;
   out.pix = nullptr; out.row_origin = 0; out.width = out_w; out.height = out_h;
@@ -1307,6 +1358,7 @@ static bool ensure_scratch(iwb200_job *job) {
 
 iwb200_job *iwb200_job_create(struct iw_context *ctx, int device) {
   if (!ctx) return nullptr;
+  dev_guard on_device(device);
   if (ctx->use_count == 0) {  // standalone use: decide the plan now; the context is consumed like in iw_process_image
     ctx->use_count++;
     if (!iwb_prepare(ctx)) return nullptr;
@@ -1366,9 +1418,9 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
   if (stream_ && stream_ != job->streams[1]) job->used_external_stream = 1;
   if (job->any_errdiff && r0 != job->errdiff_next_row && r0 != 0)
     return fail(job, "error-diffusion dither must be processed in row order from row 0");
-#if !defined(IWB_EMU)
-  cudaSetDevice(job->device);
-#endif
+  if (job->float_prepass && !job->prepass_done)
+    return fail(job, "device-resident floating-point input must be in a linear colorspace (host buffers are linearised by the library)");
+  dev_guard on_device(job->device);
   DevInput in = job->in;
   in.pix = (const uint8_t *)d_in; in.bpr = in_bpr; in.row_origin = in_row_origin;
   if (job->x0_override >= 0) in.x0 = job->x0_override;
@@ -1387,6 +1439,7 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
   }
 #endif
   if (!ensure_scratch(job)) return 0;
+  job->order_after_stream0(stream);
   const int W = out.width;
   if (job->any_errdiff && r0 == 0)
     for (int p = 0; p < job->nproc; p++)
@@ -1463,8 +1516,8 @@ int iwb200_job_read_intermediate(iwb200_job *job, int ch, float *dst, size_t cap
   if (width) *width = w;
   if (!dst) return 1;
   if (capacity < (size_t)nrows * w) return 0;
+  dev_guard on_device(job->device);
 #if !defined(IWB_EMU)
-  cudaSetDevice(job->device);
   cudaDeviceSynchronize();
 #endif
   if (job->last_path == 0) {
@@ -1537,6 +1590,46 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
   if (!iwb200_job_band_input_rows(job, r0, r1, &first, &last)) return fail(job, "invalid output row band");
   first = std::max(first, 0);
   last = std::min(last, job->phys_h - 1);
+  // float samples in a non-linear colourspace -> linear doubles, on the host cores (see job_build)
+  struct pre_buf { void *p = nullptr; bool pinned = false; ~pre_buf() { if (p && !(pinned && iwb_pinned_free(p))) free(p); } } pre;
+  if (job->float_prepass) {
+    const size_t nsamp = (size_t)job->phys_w * job->in.nch_phys, pre_bpr = nsamp * sizeof(double);
+    const size_t bytes = (size_t)(last - first + 1) * pre_bpr;
+    pre.p = iwb_pinned_alloc(bytes);
+    pre.pinned = pre.p != nullptr;
+    if (!pre.p) pre.p = malloc(bytes ? bytes : 1);
+    if (!pre.p) return fail(job, "out of memory (linearised input)");
+    const iw_context *ctx = job->ctx;
+    const int nch = job->in.nch_phys;
+    const int alpha_ch = IW_IMGTYPE_HAS_ALPHA(ctx->img1.imgtype) ? nch - 1 : -1;
+    const iw_csdescr cs = ctx->img1cs;
+    const uint8_t *src = (const uint8_t *)h_in;
+    double *dstp = (double *)pre.p;
+    const int nrows = last - first + 1;
+    auto work = [&](int ra, int rb) {
+      for (int r = ra; r < rb; r++) {
+        const uint8_t *row = src + (size_t)(first + r) * in_bpr;
+        double *d = dstp + (size_t)r * nsamp;
+        for (size_t i = 0; i < nsamp; i++) {
+          float f;
+          memcpy(&f, row + 4 * i, 4);
+          const double v = (double)f;
+          d[i] = ((int)(i % (size_t)nch) == alpha_ch) ? v : iwb_to_linear(v, &cs);
+        }
+      }
+    };
+    int nthr = (int)std::min<size_t>(16, std::max<size_t>(1, (size_t)nrows * nsamp / 65536));
+    nthr = std::min(nthr, std::max(1, (int)std::thread::hardware_concurrency()));
+    if (nthr <= 1) work(0, nrows);
+    else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nthr; t++) th.emplace_back(work, (int)((long long)nrows * t / nthr), (int)((long long)nrows * (t + 1) / nthr));
+      for (auto &t : th) t.join();
+    }
+    h_in = (const uint8_t *)pre.p - (size_t)first * pre_bpr;     // rows are addressed by their physical index below
+    in_bpr = pre_bpr;
+  }
+  job->prepass_done = job->float_prepass;
   // The device copy of the input gets a row pitch that is a multiple of 16 bytes (the TMA kernels need aligned rows);
   // the pitch conversion costs nothing: it is done by the copy engine (2-D H2D copy).
   size_t d_bpr = in_bpr;
@@ -1570,7 +1663,7 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
   // Software pipeline over output-row sub-bands: while sub-band k computes, the input rows of k+1 arrive and the
   // output rows of k-1 leave (three streams, page-locked host buffers).  The kernels take a fraction of the PCIe
   // time, so the call costs about one H2D of the image.  Sequential (error-diffusion) jobs use one sub-band.
-  cudaSetDevice(job->device);
+  dev_guard on_device(job->device);
   if (!job->streams[0])
     for (int k = 0; k < 3; k++) { cudaStream_t st; cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking); job->streams[k] = st; }
   cudaStream_t s_in = (cudaStream_t)job->streams[0], s_k = (cudaStream_t)job->streams[1], s_out = (cudaStream_t)job->streams[2];
@@ -1586,6 +1679,8 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
   // the default stream may still be uploading this job's tables
   cudaEventRecord(ev(2 * nsub), 0);
   cudaStreamWaitEvent(s_k, ev(2 * nsub), 0);
+  cudaStreamWaitEvent(s_in, ev(2 * nsub), 0);                   // (the staging buffers were allocated there too)
+  job->s0_dirty = false; job->s0_stream = (void *)s_k;
   cudaEventRecord(ev(2 * nsub + 1), s_in);       // timing origin
   int copied_to = first - 1;                     // last physical input row already requested
   bool ok = true;

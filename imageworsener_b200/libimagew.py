@@ -174,7 +174,6 @@ _SIGS = {
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
 PRODUCT_SO = os.path.join(_HERE, "libimagew_b200.so")
-REFERENCE_SO = os.path.join(REPO_ROOT, "oracle", "_ref", "libiwref.so")
 
 
 class IwError(RuntimeError):
@@ -252,11 +251,3 @@ def load_product() -> Lib:
                 "(there is no CPU fallback)")
         _cache[PRODUCT_SO] = Lib(PRODUCT_SO)
     return _cache[PRODUCT_SO]
-
-
-def load_reference() -> Lib:
-    """The unmodified reference build (oracle/_ref).  Only tests/, smoke() and bench.py's CPU-baseline
-    leg may call this."""
-    if REFERENCE_SO not in _cache:
-        _cache[REFERENCE_SO] = Lib(REFERENCE_SO)
-    return _cache[REFERENCE_SO]

@@ -863,3 +863,24 @@ done:
   rr_free(s->cache[0]); rr_free(s->cache[1]);
   return ok;
 }
+
+/* ---- synthetic input + fingerprints for bench.py's reference arm and the tests: xorshift64
+ * noise, byte = state >> 24, raster order; FNV-1a-64 of a buffer.  Kept here so that the reference arm never has to
+ * load the product library. ---- */
+void iwo_synth_xorshift(uint8_t *buf, size_t n, uint64_t seed) {
+  uint64_t s = seed;
+  for (size_t i = 0; i < n; i++) {
+    s ^= s << 13;
+    s ^= s >> 7;
+    s ^= s << 17;
+    buf[i] = (uint8_t)(s >> 24);
+  }
+}
+uint64_t iwo_fnv1a64(const uint8_t *buf, size_t n) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (size_t i = 0; i < n; i++) {
+    h ^= buf[i];
+    h *= 0x100000001b3ull;
+  }
+  return h;
+}

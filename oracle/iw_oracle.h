@@ -61,4 +61,7 @@ double iwo_from_linear(double v, int cstype, double gamma);
 uint32_t iwo_prng_nth(int seed, uint64_t n);  /* n-th draw (0-based) by direct iteration */
 int iwo_weightlist(const iwo_params *p, int dimension, int channeltype, int n_in, int n_out, double out_true,
                    int apply_bkgd_early, double bkgd_value, int *src, int *dst, double *w, int cap);
+/* synthetic input and fingerprints (bench.py --impl reference, tests) */
+void iwo_synth_xorshift(uint8_t *buf, size_t n, uint64_t seed);
+uint64_t iwo_fnv1a64(const uint8_t *buf, size_t n);
 #endif

@@ -17,10 +17,10 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def ref():
     """The unmodified reference build (oracle/_ref) -- checker only."""
-    from imageworsener_b200 import libimagew as L
-    if not os.path.exists(L.REFERENCE_SO):
+    import oracle
+    if not os.path.exists(oracle.REFERENCE_SO):
         pytest.skip("oracle/_ref/libiwref.so not built (make -C oracle ref needs /root/reference)")
-    return L.load_reference()
+    return oracle.load_reference()
 
 
 @pytest.fixture(scope="session")

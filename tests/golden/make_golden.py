@@ -28,6 +28,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import harness  # noqa: E402
 import pngmini  # noqa: E402  (tests/golden is on sys.path because this script lives there)
 from imageworsener_b200 import libimagew as L  # noqa: E402
+import oracle  # noqa: E402  (test infrastructure: the reference build / port)
 from imageworsener_b200.jobs import Job  # noqa: E402
 
 REF = os.environ.get("IW_REFERENCE", "/root/reference")
@@ -84,7 +85,7 @@ def expand_runtest():
 
 
 def main():
-    ref = L.load_reference()
+    ref = oracle.load_reference()
     cases_meta = []
     blob = {}
     skipped = []

@@ -19,6 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 from imageworsener_b200 import _build, configs, libimagew as L  # noqa: E402
+import oracle  # noqa: E402  (test infrastructure: the reference build / port)
 
 OUT = os.path.join(HERE, "known_answers.json")
 
@@ -26,7 +27,7 @@ OUT = os.path.join(HERE, "known_answers.json")
 def main():
     names = sys.argv[1:] or ["cfg4auto", "cfg4box", "cfg2", "cfg3", "cfg5"]
     helper = L.Lib(_build.build_emulator())   # only for the synth/hash helpers (plain host C)
-    ref = L.load_reference()
+    ref = oracle.load_reference()
     known = json.load(open(OUT)) if os.path.exists(OUT) else {}
     for name in names:
         cfg = configs.get(name)

@@ -9,6 +9,7 @@ import os
 import numpy as np
 
 from imageworsener_b200 import libimagew as L
+import oracle  # noqa: E402  (test infrastructure: the reference build / port)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -187,7 +188,7 @@ class OraclePort:
         ctx.p.gray_w[:] = [r / tot, g / tot, b / tot]
 
     def iw_get_profile_by_fmt(self, fmt):
-        return L.load_reference().iw_get_profile_by_fmt(fmt) if os.path.exists(L.REFERENCE_SO) else _PROFILES[fmt]
+        return oracle.load_reference().iw_get_profile_by_fmt(fmt) if os.path.exists(oracle.REFERENCE_SO) else _PROFILES[fmt]
 
     def iw_set_output_profile(self, ctx, n): ctx.p.profile = n
     def iw_set_output_depth(self, ctx, bps): ctx.p.out_depth_req = bps

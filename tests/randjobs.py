@@ -111,3 +111,29 @@ def make(seed: int, max_in: int = 60, max_out: int = 90, allow_errdiff: bool = T
     elif q < 0.25:
         outfmt = "miff"
     return inp, " ".join(a), outfmt
+
+
+def make_float(seed: int, **kw):
+    """A random job whose input image holds 32-bit floating-point samples (src/imagew.h:387-390: native byte order),
+    in a linear or a non-linear colourspace.  Sample values lie in [0, 1.25]: mostly code/255 of the integer job's
+    bytes, some beyond 1.0 (HDR-ish input; the pipeline clamps late, src/imagew-main.c:684-685)."""
+    inp, args, outfmt = make(seed, allow_errdiff=kw.pop("allow_errdiff", False), **kw)
+    r = np.random.default_rng(seed + 77_000)
+    nch = L.imgtype_num_channels(inp["imgtype"])
+    w, h = inp["width"], inp["height"]
+    src = r.integers(0, 256, size=(h, w * nch)).astype(np.float32) / np.float32(255.0)
+    if r.random() < 0.5:
+        src *= np.float32(1.25)
+    if r.random() < 0.3:
+        src[: max(1, h // 3)] = np.float32(r.choice([0.0, 1.0, 0.5]))
+    if nch in (2, 4):                                                # alpha stays in [0, 1]
+        src.reshape(h, w, nch)[:, :, nch - 1] = np.minimum(src.reshape(h, w, nch)[:, :, nch - 1], np.float32(1.0))
+    pad = int(r.integers(0, 2)) * 4
+    rows = np.zeros((h, w * nch * 4 + pad), np.uint8)
+    rows[:, : w * nch * 4] = src.view(np.uint8).reshape(h, w * nch * 4)
+    inp = dict(inp, bit_depth=32, sampletype=L.IW_SAMPLETYPE_FLOATINGPOINT, rows=rows)
+    inp.pop("maxcodes", None)
+    inp["cs"] = [None, ("linear", 0.0), ("gamma", 2.2), ("rec709", 0.0), ("srgb", 0.0)][r.integers(0, 5)]
+    if inp["cs"] is None:
+        inp.pop("cs")                                                # the context default: sRGB
+    return inp, args, outfmt

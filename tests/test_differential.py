@@ -11,8 +11,8 @@ import randjobs
 from imageworsener_b200.jobs import Job
 
 
-def _one(lib, ref, seed, **kw):
-    inp, args, outfmt = randjobs.make(seed, **kw)
+def _one(lib, ref, seed, maker=randjobs.make, **kw):
+    inp, args, outfmt = maker(seed, **kw)
     ja = Job.parse(args, outfmt=outfmt, disable_all_opt=True)
     jb = Job.parse(args, outfmt=outfmt, disable_all_opt=True)
     a = harness.run_job(lib, inp, ja)
@@ -45,3 +45,16 @@ def test_cuda_matches_reference_small(prod, ref, seed):
 @pytest.mark.parametrize("seed", range(2000, 2060))
 def test_cuda_matches_reference_medium(prod, ref, seed):
     _one(prod, ref, seed, max_in=700, max_out=900, allow_errdiff=False)
+
+
+# floating-point input samples (reference: get_raw_sample_flt32 + x_to_linear_sample per sample,
+# src/imagew-main.c:53-66, :129-145, :348-372), in linear and non-linear colourspaces, with and without alpha
+@pytest.mark.parametrize("seed", range(5000, 5060))
+def test_host_logic_float_input(emu, ref, seed):
+    _one(emu, ref, seed, maker=randjobs.make_float)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(5100, 5180))
+def test_cuda_float_input(prod, ref, seed):
+    _one(prod, ref, seed, maker=randjobs.make_float)

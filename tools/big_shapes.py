@@ -2,7 +2,8 @@
 import sys, numpy as np
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from imageworsener_b200 import configs, libimagew as L
-prod, ref = L.load_product(), L.load_reference()
+import oracle  # noqa: E402  (test infrastructure: the reference build / port)
+prod, ref = L.load_product(), oracle.load_reference()
 RGB, GRAY = L.IW_IMGTYPE_RGB, L.IW_IMGTYPE_GRAY
 bad = 0
 for name, iw, ih, typ, depth, ow, oh, extra, opts in [

@@ -14,6 +14,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from imageworsener_b200 import configs, libimagew as L  # noqa: E402
+import oracle  # noqa: E402  (test infrastructure: the reference build / port)
 
 
 def main():
@@ -25,7 +26,7 @@ def main():
     prod = L.load_product()
     ok = True
     if not args.skip_parity:
-        ref = L.load_reference()
+        ref = oracle.load_reference()
         shapes = [("cfg2", 16), ("cfg2", 4)] if args.quick else [("cfg2", 16), ("cfg2", 4), ("cfg4box", 1), ("cfg4auto", 2)]
         for name, scale in shapes:
             cfg = configs.get(name, scale)

@@ -13,12 +13,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from imageworsener_b200 import configs, libimagew as L  # noqa: E402
+import oracle  # noqa: E402  (test infrastructure: the reference build / port)
 from test_stream2 import _enlargement_case, _near_integer_case  # noqa: E402
 
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 300
-    prod, ref = L.load_product(), L.load_reference()
+    prod, ref = L.load_product(), oracle.load_reference()
     bad = samples = 0
     t0 = time.time()
     for seed in range(5000, 5000 + n):
