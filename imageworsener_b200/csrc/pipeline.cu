@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include "fused.cuh"
 #include "stream2.cuh"
+#include "stream3.cuh"
 #endif
 
 // ------------------------------------------------------------------------------------------------------
@@ -236,6 +237,7 @@ struct iwb200_job {
   int errdiff_next_row = 0;
   // where the FP32 intermediate of the last chunk lives (iwb200_job_read_intermediate)
   int last_path = -1, last_c0 = 0, last_c1 = 0, last_sh = 0;
+  int last_gen = 0;                 // kernel generation of the last launch (0 generic, 1 / 2 streaming, 3 fused)
   int x0_override = -1;             // set by run_host while its device copy holds only the cropped columns
   int float_prepass = 0;            // float input in a non-linear colourspace: run_host linearises it on the host first
   int prepass_done = 0;             // (set by run_host around its run_device calls)
@@ -245,8 +247,8 @@ struct iwb200_job {
   int profiling = 0;
   struct timed { int which; void *a, *b; };
   std::vector<timed> pending;
-  int stat_n[6] = {0, 0, 0, 0, 0, 0};
-  double stat_ms[6] = {0, 0, 0, 0, 0, 0};
+  int stat_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double stat_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::string key;            // plan-cache key (empty: not cacheable)
   int reused = 0, used_external_stream = 0;
   void *streams[3] = {nullptr, nullptr, nullptr};   // run_host pipeline: copy-in, compute, copy-out
@@ -256,6 +258,9 @@ struct iwb200_job {
   void *d_out = nullptr; size_t d_out_bytes = 0;
 #if !defined(IWB_EMU)
   FastPlan fused;
+  std::vector<std::unique_ptr<VH3State>> vh3;    // fused-kernel state per row range (stream3.cuh)
+  int gen3 = 1;                                 // 0: never, 1: when the launch is large enough, 2: whenever supported
+  int gen3_nv = 0, gen3_seg = 0;
   struct s2_tables { Sched2 v, h; Quant2 q[4]; };
   std::unique_ptr<s2_tables> s2_store;
 #endif
@@ -860,6 +865,9 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
       if (const char *o2 = iwb_option(ctx, "cuda:seg2")) f->seg2 = std::max(4, atoi(o2) & ~3);
       if (const char *o2 = iwb_option(ctx, "cuda:uniform")) f->uniform = atoi(o2) != 0;
       if (const char *o2 = iwb_option(ctx, "cuda:overlap")) f->overlap = std::max(1, std::min(32, atoi(o2)));
+      if (const char *o2 = iwb_option(ctx, "cuda:gen")) { const int g = atoi(o2); job->gen3 = g == 3 ? 2 : (g == 2 ? 0 : 1); }
+      if (const char *o2 = iwb_option(ctx, "cuda:nv")) job->gen3_nv = atoi(o2);
+      if (const char *o2 = iwb_option(ctx, "cuda:seg3")) job->gen3_seg = std::max(16, atoi(o2) & ~3);
       if (rep && !f->same_tables) ok = false;                    // (one decision serves the three bytes unless the dither is random)
       f->v2 = ok ? 1 : 0;
     }
@@ -934,6 +942,42 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
       vj.S = f->SV; vj.first_host = f->vfirst.data(); vj.last_host = f->vlast.data(); vj.strip_override = f->strip2; vj.allow_uniform = f->uniform;
       job->last_path = 2; job->last_c0 = c0; job->last_c1 = c1; job->last_sh = hp.sh; job->last_pitch = pitch; job->last_inter = inter;
       if (nsub > 1 && i >= 2) cudaStreamWaitEvent(sv, (cudaEvent_t)f->ev[64 + i - 2], 0);   // this half was read by H(i-2)
+      // generation 3: both passes in one persistent kernel (stream3.cuh), when the launch is large enough to fill it
+      if (nsub == 1 && job->gen3 && iwb3_supported(f->SV, f->SH, nch, f->nco, f->epi, f->depth16) &&
+          (job->gen3 == 2 || ((long long)(c1 - c0) * vp.ncols >= (8ll << 20) && out.width >= 512))) {
+        VH3State *stt = nullptr;
+        for (auto &u : job->vh3) if (u->c0 == c0 && u->c1 == c1) stt = u.get();
+        if (!stt) {
+          if (job->vh3.size() >= 64) {                           // (callers that keep changing the row range: start over)
+            cudaStreamSynchronize(sv);
+            for (auto &u : job->vh3) if (u->dev) cudaFreeAsync(u->dev, sv);
+            job->vh3.clear();
+          }
+          job->vh3.emplace_back(new VH3State()); stt = job->vh3.back().get();
+        }
+        bool launched = false;
+        {
+          prof_scope ps(job, 6, stream);
+          iwb3_run(vj, hj, stt, job->gen3_nv, job->gen3_seg, sv, &launched);
+        }
+        if (launched) {
+          g_launches++;
+          job->last_gen = 3;
+          if (job->negate) {
+            PostParams pp;
+            pp.out = out; pp.row0 = c0; pp.row1 = c1; pp.negate = 1; pp.alpha_ch = -1; pp.clear_transparent = 0;
+            for (int c = 0; c < 4; c++) pp.maxcode[c] = c < job->ctx->out_nch ? job->ctx->out_ci[c].maxcode : 0;
+            prof_scope ps(job, 4, (iwb_stream)sv);
+            launch<PostBody>(pp, (size_t)(c1 - c0) * out.width, (iwb_stream)sv);
+          }
+          continue;
+        }
+        if (job->profiling && !job->pending.empty()) {           // nothing ran inside that bracket
+          cudaEventDestroy((cudaEvent_t)job->pending.back().a); cudaEventDestroy((cudaEvent_t)job->pending.back().b);
+          job->pending.pop_back();
+        }
+      }
+      job->last_gen = 2;
       {
         prof_scope ps(job, 5, stream);
         if (!iwb2_run_v(vj, sv)) return fail(job, "fast path: no vertical kernel variant (gen 2)");
@@ -967,6 +1011,7 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
   for (int c0 = r0; c0 < r1; c0 += f->chunk_rows) {
     const int c1 = std::min(r1, c0 + f->chunk_rows);
     job->last_path = 1; job->last_c0 = c0; job->last_c1 = c1; job->last_pitch = f->pitch_j; job->last_inter = f->interT;
+    job->last_gen = 1;
     VStreamParams vp;
     vp.src = in.pix; vp.bpr = in.bpr; vp.row_origin = in.row_origin; vp.y0 = in.y0;
     vp.x0_bytes = (size_t)in.x0 * nch; vp.ncols = job->in_w * nch; vp.lut = f->lut; vp.sc = f->sv;
@@ -1015,6 +1060,9 @@ static void job_free(iwb200_job *job) {
   for (void *e : job->events) cudaEventDestroy((cudaEvent_t)e);
   for (void *e : job->fused.ev) cudaEventDestroy((cudaEvent_t)e);
   if (job->fused.aux_stream) cudaStreamDestroy((cudaStream_t)job->fused.aux_stream);
+#endif
+#if !defined(IWB_EMU)
+  for (auto &u : job->vh3) if (u->dev) cudaFreeAsync(u->dev, 0);
 #endif
   for (void *p : job->allocs) dev_free(p);
   dev_free(job->d_in);
@@ -1449,6 +1497,7 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
     const int c1 = std::min(r1, c0 + job->chunk_rows);
     const size_t rows = c1 - c0;
     job->last_path = 0; job->last_c0 = c0; job->last_c1 = c1;
+    job->last_gen = 0;
     // vertical pass, all channels
     VPassParams vp;
     vp.in = in; vp.cm = job->cm; vp.nch = job->nproc; vp.in_w = job->in_w; vp.row0 = c0; vp.row1 = c1;
@@ -1547,14 +1596,15 @@ int iwb200_job_read_intermediate(iwb200_job *job, int ch, float *dst, size_t cap
 }
 
 void iwb200_job_set_profiling(iwb200_job *job, int on) { if (job) job->profiling = on; }
+int iwb200_job_last_kernel_generation(const iwb200_job *job) { return job ? job->last_gen : -1; }
 void iwb200_job_reset_stats(iwb200_job *job) {
   if (!job) return;
   int n; double ms;
   iwb200_job_kernel_stats(job, 0, &n, &ms);  // drains pending events
-  for (int k = 0; k < 6; k++) { job->stat_n[k] = 0; job->stat_ms[k] = 0; }
+  for (int k = 0; k < 8; k++) { job->stat_n[k] = 0; job->stat_ms[k] = 0; }
 }
 int iwb200_job_kernel_stats(iwb200_job *job, int which, int *launches, double *total_ms) {
-  if (!job || which < 0 || which >= 6) return 0;
+  if (!job || which < 0 || which >= 8) return 0;
 #if !defined(IWB_EMU)
   for (auto &t : job->pending) {
     cudaEvent_t a = (cudaEvent_t)t.a, b = (cudaEvent_t)t.b;

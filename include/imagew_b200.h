@@ -337,9 +337,13 @@ int iwb200_job_read_intermediate(iwb200_job *job, int ch, float *dst, size_t cap
 
 /* Per-kernel device timing.  When enabled, every launch of this job is bracketed by CUDA events on the launching
  * stream; iwb200_job_kernel_stats() synchronises and returns, for kernel class `which` (0 vertical pass,
- * 1 horizontal pass + epilogue, 2 PRNG fill, 3 error diffusion, 4 post, 5 fused tile kernel), the number of
- * launches and their summed duration in ms since the last reset. */
+ * 1 horizontal pass + epilogue, 2 PRNG fill, 3 error diffusion, 4 post, 5 vertical streaming kernel, 6 fused
+ * vertical + horizontal kernel), the number of launches and their summed duration in ms since the last reset. */
 void iwb200_job_set_profiling(iwb200_job *job, int on);
+/* Kernel generation the job's last launch took: 0 generic per-sample kernels, 1 / 2 streaming kernels of the first /
+ * second generation (two kernels per chunk), 3 the fused persistent vertical + horizontal kernel; -1 for a null job.
+ * Context option "cuda:gen" = 1 | 2 | 3 forces a generation where the job allows it (3: also for small launches). */
+int iwb200_job_last_kernel_generation(const iwb200_job *job);
 int iwb200_job_kernel_stats(iwb200_job *job, int which, int *launches, double *total_ms);
 void iwb200_job_reset_stats(iwb200_job *job);
 
