@@ -34,7 +34,7 @@ from imageworsener_b200 import configs, libimagew as L  # noqa: E402  (the refer
 #                                                                  # descriptions and the ctypes binding class from it)
 
 METRIC = "output Mpix/s, 8K->4K Lanczos3 linear-light RGB8 + ordered dither"
-KERNEL_CLASSES = ["v_pass_generic", "h_pass_epilogue", "prng_fill", "errdiff", "post", "v_pass_stream"]
+KERNEL_CLASSES = ["v_pass_generic", "h_pass_epilogue", "prng_fill", "errdiff", "post", "v_pass_stream", "vh_fused"]
 # measured FP64 issue rate for independent DMUL+DADD pairs.  MEASURED_PEAKS.json has no FP64 entry: this is the
 # builder's own microbenchmark (tools/fp64_peak.cu, profiles/r1_fp64_peak.txt), consistent with 148 SMs x 64 lanes x
 # 1.965 GHz = 18.6 T; the JSON line says so (`fp64.peak_source`)
@@ -308,6 +308,7 @@ def main():
     dll.iwb200_job_set_profiling.argtypes = [C.c_void_p, C.c_int]
     dll.iwb200_job_reset_stats.argtypes = [C.c_void_p]
     dll.iwb200_job_kernel_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    dll.iwb200_job_last_kernel_generation.argtypes = [C.c_void_p]
     dll.iwb200_job_last_error.restype = C.c_char_p
     dll.iwb200_job_last_error.argtypes = [C.c_void_p]
 
@@ -404,6 +405,7 @@ def main():
         if n.value:
             stats[nm] = {"launches_per_step": n.value / prof_steps, "ms_per_step": ms.value / prof_steps}
     dll.iwb200_job_set_profiling(job, 0)
+    kernel_generation = int(dll.iwb200_job_last_kernel_generation(job))
     dom = max(stats, key=lambda k: stats[k]["ms_per_step"])
     alg_bytes_step = cfg.in_bytes + out_bytes                        # read input once + write output once
     lp = stats[dom]["launches_per_step"]
@@ -472,7 +474,7 @@ def main():
                            "sharding": ("one image split into output-row bands, gathered to rank 0 with NCCL" if band_mode else
                                         "one image per GPU, no data-path collective") if world > 1 else "single GPU",
                            "l2_defeat": f"{nbuf} rotating input/output buffer sets ({nbuf * (cfg.in_bytes + out_bytes) / 1e6:.0f} MB > 126 MB L2)",
-                           "kernel_generation": int(info.uses_fused_kernel), "host_numa_binding": numa},
+                           "kernel_generation": kernel_generation, "host_numa_binding": numa},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)

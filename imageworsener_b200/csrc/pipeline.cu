@@ -64,7 +64,12 @@ static bool dev_d2h(void *h, const void *d, size_t n, iwb_stream s, std::string 
 }
 static bool dev_zero(void *d, size_t n, iwb_stream s) { return cudaMemsetAsync(d, 0, n, s) == cudaSuccess; }
 static bool dev_sync(iwb_stream s, std::string &err) {
-  if (const char *m = dev_check(cudaStreamSynchronize(s))) { err = std::string("kernel execution: ") + m; return false; }
+  if (const char *m = dev_check(cudaStreamSynchronize(s))) {
+    err = std::string("kernel execution: ") + m;
+    const std::string d = iwb3_debug_text();                    // (a fused-kernel warp that gave up waiting says why)
+    if (!d.empty()) { err += "; "; err += d; fprintf(stderr, "%s\n", d.c_str()); }
+    return false;
+  }
   return true;
 }
 template <class Body, class P>
@@ -239,6 +244,7 @@ struct iwb200_job {
   int last_path = -1, last_c0 = 0, last_c1 = 0, last_sh = 0;
   int last_gen = 0;                 // kernel generation of the last launch (0 generic, 1 / 2 streaming, 3 fused)
   int x0_override = -1;             // set by run_host while its device copy holds only the cropped columns
+  iwb_timings *tm_sink = nullptr;   // where run_host reports its phase times (default: the context's record)
   int float_prepass = 0;            // float input in a non-linear colourspace: run_host linearises it on the host first
   int prepass_done = 0;             // (set by run_host around its run_device calls)
   size_t last_pitch = 0;
@@ -1597,6 +1603,16 @@ int iwb200_job_read_intermediate(iwb200_job *job, int ch, float *dst, size_t cap
 
 void iwb200_job_set_profiling(iwb200_job *job, int on) { if (job) job->profiling = on; }
 int iwb200_job_last_kernel_generation(const iwb200_job *job) { return job ? job->last_gen : -1; }
+int iwb200_debug_fused_trap(char *buf, int buflen) {
+#if !defined(IWB_EMU)
+  const std::string d = iwb3_debug_text();
+  if (buf && buflen > 0) { strncpy(buf, d.c_str(), (size_t)buflen - 1); buf[buflen - 1] = 0; }
+  return (int)d.size();
+#else
+  if (buf && buflen > 0) buf[0] = 0;
+  return 0;
+#endif
+}
 void iwb200_job_reset_stats(iwb200_job *job) {
   if (!job) return;
   int n; double ms;
@@ -1702,7 +1718,7 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
   if (job->d_in_bytes < in_bytes) { dev_free(job->d_in); job->d_in = dev_alloc(in_bytes, job->err); job->d_in_bytes = in_bytes; }
   if (job->d_out_bytes < out_bytes) { dev_free(job->d_out); job->d_out = dev_alloc(out_bytes, job->err); job->d_out_bytes = out_bytes; }
   if (!job->d_in || !job->d_out) { job->d_in_bytes = job->d_out_bytes = 0; return 0; }
-  iwb_timings &tm = job->ctx->timings;
+  iwb_timings &tm = job->tm_sink ? *job->tm_sink : job->ctx->timings;
 #if defined(IWB_EMU)
   (void)tm; (void)col_off; (void)row_bytes;
   if (!dev_h2d(job->d_in, (const uint8_t *)h_in + (size_t)first * in_bpr, in_bytes, 0, job->err)) return 0;
@@ -1797,6 +1813,52 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
   cudaEventDestroy(done);
   return 1;
 #endif
+}
+
+
+// One image on several GPUs (context option cuda:devices, process.cpp).  The job is split into output-row bands, one per
+// listed device; each band has its own job (plan tables on its device), its own host thread and stream set, copies only
+// its input rows + filter halo host -> device and writes its output rows device -> host straight into the caller's
+// buffer, so the PCIe links of the devices work in parallel and nothing is exchanged between GPUs.  Dither phase,
+// checkerboard phase and PRNG draw index are absolute coordinates, so the bands concatenate bit-exactly.
+// The same device may be listed more than once (several bands in flight on one GPU).
+int iwb200_run_host_multi(struct iw_context *ctx, const int *devices, int ndev, const void *h_in, size_t in_bpr, void *h_out, size_t out_bpr) {
+  if (!ctx || ndev < 1) return 0;
+  const int out_h = ctx->img2.height;
+  ndev = std::max(1, std::min(ndev, std::max(1, out_h / 32)));  // (at least 32 rows per band)
+  std::vector<iwb200_job *> jobs(ndev, nullptr);
+  bool ok = true;
+  for (int i = 0; i < ndev && ok; i++) {                        // (sequential: job creation reports errors on the context)
+    jobs[i] = iwb200_job_create(ctx, devices[i]);
+    if (!jobs[i]) ok = false;
+    else if (!jobs[i]->info.bandable) {
+      iw_set_error(ctx, "CUDA backend: cuda:devices needs a job that can be split into row bands; error-diffusion dithering cannot");
+      ok = false;
+    }
+  }
+  std::vector<iwb_timings> tms(ndev);
+  std::vector<int> res(ndev, 0);
+  if (ok) {
+    std::vector<std::thread> th;
+    for (int i = 0; i < ndev; i++) {
+      // band boundaries on multiples of 32 rows (whole groups of the horizontal kernels)
+      int r0 = (int)(((long long)out_h * i / ndev) / 32 * 32), r1 = i + 1 == ndev ? out_h : (int)(((long long)out_h * (i + 1) / ndev) / 32 * 32);
+      jobs[i]->tm_sink = &tms[i];
+      th.emplace_back([&, i, r0, r1]() {
+        res[i] = r1 > r0 ? iwb200_job_run_host(jobs[i], h_in, in_bpr, (uint8_t *)h_out + (size_t)r0 * out_bpr, out_bpr, r0, r1) : 1;
+      });
+    }
+    for (auto &t : th) t.join();
+    for (int i = 0; i < ndev; i++) {
+      jobs[i]->tm_sink = nullptr;
+      if (!res[i]) { ok = false; iw_set_errorf(ctx, "CUDA backend (device %d): %s", devices[i], iwb200_job_last_error(jobs[i])); }
+      ctx->timings.h2d_ms = std::max(ctx->timings.h2d_ms, tms[i].h2d_ms);
+      ctx->timings.kernel_ms = std::max(ctx->timings.kernel_ms, tms[i].kernel_ms);
+      ctx->timings.d2h_ms = std::max(ctx->timings.d2h_ms, tms[i].d2h_ms);
+    }
+  }
+  for (iwb200_job *j : jobs) if (j) iwb200_job_destroy(j);
+  return ok ? 1 : 0;
 }
 
 }  // extern "C"

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "iwb_internal.h"
 
@@ -59,6 +60,10 @@ double now_ms() {
 
 }  // namespace
 
+static int finish_result(struct iw_context *ctx, int r0, int r1);
+extern "C" int iwb200_run_host_multi(struct iw_context *ctx, const int *devices, int ndev, const void *h_in, size_t in_bpr, void *h_out,
+                                     size_t out_bpr);
+
 extern "C" {
 
 int iw_process_image(struct iw_context *ctx) {
@@ -82,6 +87,41 @@ int iw_process_image(struct iw_context *ctx) {
 
   int device = 0;
   if (const char *d = iwb_option(ctx, "cuda:device")) device = atoi(d);
+  // "cuda:devices" = "0,1,2,...": the image is split into output-row bands, one per listed device (pipeline.cu:
+  // iwb200_run_host_multi); a single entry is the same as cuda:device
+  std::vector<int> devices;
+  if (const char *dl = iwb_option(ctx, "cuda:devices")) {
+    for (const char *q = dl; *q;) {
+      char *end = nullptr;
+      const long v = strtol(q, &end, 10);
+      if (end == q || v < 0 || v > 1023) { devices.clear(); break; }
+      devices.push_back((int)v);
+      q = end;
+      while (*q == ',' || *q == ' ') q++;
+    }
+    if (devices.empty() || devices.size() > 64) {
+      iw_set_error(ctx, "CUDA backend: cuda:devices must be a comma-separated list of device ordinals");
+      return 0;
+    }
+    if (devices.size() == 1) { device = devices[0]; devices.clear(); }
+    else if (iwb_option(ctx, "cuda:band")) {
+      iw_set_error(ctx, "CUDA backend: cuda:devices and cuda:band cannot be combined");
+      return 0;
+    }
+  }
+  if (!devices.empty()) {
+    ctx->img2.bpr = iw_calc_bytesperrow(ctx->img2.width, ctx->img2.bit_depth * ctx->out_nch);
+    ctx->img2.pixels = (iw_byte *)iw_malloc_large(ctx, ctx->img2.bpr, (size_t)ctx->img2.height);
+    if (!ctx->img2.pixels) return 0;
+    ctx->band_row0 = 0;
+    ctx->band_row1 = ctx->img2.height;
+    ctx->timings.plan_ms = now_ms() - t0;
+    if (!iwb200_run_host_multi(ctx, devices.data(), (int)devices.size(), ctx->img1.pixels, ctx->img1.bpr, ctx->img2.pixels, ctx->img2.bpr)) {
+      if (!ctx->error_flag) iw_set_error(ctx, "CUDA backend: multi-device run failed");
+      return 0;
+    }
+    return finish_result(ctx, 0, ctx->img2.height);
+  }
   iwb200_job *job = iwb200_job_create(ctx, device);
   if (!job) {
     if (!ctx->error_flag) iw_set_error(ctx, "CUDA backend: could not build the processing plan");
@@ -125,6 +165,13 @@ int iw_process_image(struct iw_context *ctx) {
   iwb200_job_destroy(job);
   if (!ok) return 0;
 
+  return finish_result(ctx, r0, r1);
+}
+
+}  // extern "C"
+
+// what follows the kernels: background-colour label and the result view handed out by iw_get_output_image
+static int finish_result(struct iw_context *ctx, int r0, int r1) {
   make_output_label(ctx);
 
   // The reference's post-pass optimiser (src/imagew-opt.c) is outside this library's scope; the result view
@@ -142,6 +189,8 @@ int iw_process_image(struct iw_context *ctx) {
   }
   return 1;
 }
+
+extern "C" {
 
 void iwb200_detach_input_image(struct iw_context *ctx) {
   if (ctx) ctx->img1.pixels = nullptr;

@@ -8,6 +8,8 @@
 // still in L2.  See stream3_dev.cuh for the synchronisation; the arithmetic is generation 2's, statement for statement
 // (reference: src/imagew-resize.c:346-361, src/imagew-main.c:831-927, :929-1155).
 #pragma once
+#include <string>
+
 #include "stream2.cuh"
 
 #if !defined(IWB_EMU)
@@ -28,6 +30,7 @@ struct VH3Sync {
   int ncb, cbw;
   int gen;
   int v_base, h_base;            // first ticket of this launch
+  int *dbg;                      // diagnostic slot (page-locked host memory, device-visible): [0] = records, [8 + 8k...] = record k
 };
 
 struct VH3Params {
@@ -53,6 +56,10 @@ struct VH3State {
   int nv = 0, grid = 0;
   bool order_uploaded = false;
 };
+// The diagnostic slot of the current device (128 ints of mapped page-locked memory, allocated on first use), and its
+// content as text after a failed launch (empty if nothing was recorded).
+int *iwb3_debug_slot();
+std::string iwb3_debug_text();
 
 bool iwb3_supported(int SV, int SH, int nch, int nco, int epi, int depth16);
 // false: not applicable to this launch (the caller falls back to the two-kernel path) or launch problem (err set)

@@ -30,18 +30,60 @@ __device__ __forceinline__ int s3_ld_acquire(const int *p) {
 __device__ __forceinline__ void s3_red_release(int *p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// a fresh set of pipeline barriers for the next item (every copy of the previous item has been waited for)
-__device__ __forceinline__ void s3_reset_bars(unsigned bar0, int lane, bool first) {
-  __syncwarp();
+// Every wait of this kernel is bounded: a warp that has waited ~4 s (wall clock) for a copy or for another warp's
+// announcement records what it was waiting for in the launch's diagnostic slot (page-locked host memory) and traps, so a
+// protocol bug ends the launch with an error instead of hanging the device.
+__device__ __forceinline__ unsigned long long s3_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+static __device__ __noinline__ void s3_die(int *dbg, int what, int a, int b, int c, int d) {
+  if (dbg) {
+    const int k = atomicAdd(dbg, 1);
+    if (k < 15) {
+      volatile int *r = dbg + 8 + 8 * k;
+      r[0] = what; r[1] = (int)blockIdx.x; r[2] = (int)(threadIdx.x >> 5); r[3] = a; r[4] = b; r[5] = c; r[6] = d;
+    }
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void s3_mbar_wait(unsigned bar, unsigned parity, int *dbg, int what, int a, int b) {
+  unsigned long long t0 = 0;
+  for (unsigned spins = 0;; spins++) {
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((spins & 1023) == 1023) {
+      const unsigned long long t = s3_now();
+      if (!t0) t0 = t;
+      else if (t - t0 > 4000000000ull) s3_die(dbg, what, a, b, (int)parity, (int)spins);
+    }
+  }
+}
+// The pipeline barriers of a warp live for the whole kernel.  Every copy a warp starts is waited for exactly once (both
+// paths of both passes), so a slot's barrier alternates fill, wait, fill, wait ... across items, and one phase bit per slot
+// (`ph`, a register that travels with the warp from item to item) is all the bookkeeping needed.
+__device__ __forceinline__ void s3_init_bars(unsigned bar0, int lane) {
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < 8; s++) {
-      if (!first) s3_mbar_inval(bar0 + 8 * s);
-      s2_mbar_init(bar0 + 8 * s, 1);
-    }
+    for (int s = 0; s < 8; s++) s2_mbar_init(bar0 + 8 * s, 1);
     s2_fence_async();
   }
   __syncwarp();
+}
+__device__ __forceinline__ void s3_slot_wait(unsigned bar0, int slot, unsigned &ph, int *dbg, int what, int a, int b) {
+  s3_mbar_wait(bar0 + 8 * slot, (ph >> slot) & 1u, dbg, what, a, b);
+  ph ^= 1u << slot;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -50,7 +92,7 @@ __device__ __forceinline__ void s3_reset_bars(unsigned bar0, int lane, bool firs
 template <int S, int STEP, bool D16>
 __device__ __forceinline__ void s3_v_item(const V2Params &p, const CUtensorMap *tmap, const CUtensorMap *tmap_u, const VH3Sync &sy,
                                           unsigned char *wbase, int ring_bytes, const double *lut_s, int wc, int o0, int o1, bool uni,
-                                          bool first_item) {
+                                          unsigned &ph) {
   constexpr int SS = (S + 1) & ~1;
   constexpr int G = iwb2_v_g(STEP), NST = IWB2_V_NST;
   constexpr int TW = D16 ? 256 : 128;
@@ -96,7 +138,7 @@ __device__ __forceinline__ void s3_v_item(const V2Params &p, const CUtensorMap *
       s2_bulk_g2s(dst + GU * TW, p.sc.w + (ptrdiff_t)(R0 + n * GU) * SS, GU * SS * 8, bar);
     }
   };
-  s3_reset_bars(bar0, lane, first_item);
+  __syncwarp();                                                 // (every lane is done with the previous item's ring and window table)
   if (uni) {
 #pragma unroll
     for (int s = 0; s < NSTU; s++)
@@ -190,8 +232,7 @@ __device__ __forceinline__ void s3_v_item(const V2Params &p, const CUtensorMap *
 
   if (STEP > 0 && uni) {
     int slot = 0;
-    unsigned par = 0;
-    s2_mbar_wait(bar0, 0);
+    s3_slot_wait(bar0, 0, ph, sy.dbg, 1, wc, o0);
     double vc[4];
     {
       const word x0 = ring_word(ring0 + lane * (TW / 32));
@@ -201,13 +242,12 @@ __device__ __forceinline__ void s3_v_item(const V2Params &p, const CUtensorMap *
     word xn = ring_word(ring0 + lane * (TW / 32) + TW);
     for (int cyc = 0; cyc < ncyc; cyc++) {
       const int nslot = slot + 1 == NSTU ? 0 : slot + 1;
-      const unsigned npar = nslot == 0 ? par ^ 1 : par;
       const unsigned sb = ring0 + slot * STAGE_U + lane * (TW / 32), sbn = ring0 + nslot * STAGE_U + lane * (TW / 32);
       const unsigned wb = ring0 + slot * STAGE_U + GU * TW;
       const int og = og0 + cyc * S;
 #pragma unroll
       for (int r = 0; r < GU; r++) {
-        if (r == GU - 2) s2_mbar_wait(bar0 + 8 * nslot, npar);
+        if (r == GU - 2) s3_slot_wait(bar0, nslot, ph, sy.dbg, 2, wc, cyc);
         const word xcur = xn;
         xn = ring_word(r + 2 < GU ? sb + (r + 2) * TW : sbn + (r + 2 - GU) * TW);
         taps(vc, xcur, wb + r * SS * 8);
@@ -216,14 +256,12 @@ __device__ __forceinline__ void s3_v_item(const V2Params &p, const CUtensorMap *
       __syncwarp();
       if (cyc + NSTU <= ncyc) fill_u(cyc + NSTU, slot);
       slot = nslot;
-      par = npar;
     }
     return;
   }
 
   int ld_stage = 0, ld_slot = 0, w_slot = 0;
-  unsigned parity = 0;
-  s2_mbar_wait(bar0, 0);
+  s3_slot_wait(bar0, 0, ph, sy.dbg, 3, wc, o0);
   unsigned pin = ring0 + lane * (TW / 32);
   unsigned pin_end = pin + G * TW;
   unsigned pw = ring0 + G * TW;
@@ -232,8 +270,8 @@ __device__ __forceinline__ void s3_v_item(const V2Params &p, const CUtensorMap *
     __syncwarp();
     if (ld_stage >= 1 && ld_stage - 1 + NST < nstg) fill(ld_stage - 1 + NST, ld_slot == 0 ? NST - 1 : ld_slot - 1);
     ld_stage++;
-    if (++ld_slot == NST) { ld_slot = 0; parity ^= 1; }
-    if (ld_stage < nstg) s2_mbar_wait(bar0 + 8 * ld_slot, parity);
+    if (++ld_slot == NST) ld_slot = 0;
+    if (ld_stage < nstg) s3_slot_wait(bar0, ld_slot, ph, sy.dbg, 4, wc, ld_stage);
     pin = ring0 + ld_slot * STAGE + lane * (TW / 32);
     pin_end = pin + G * TW;
   };
@@ -279,9 +317,9 @@ __device__ __forceinline__ void s3_v_item(const V2Params &p, const CUtensorMap *
 // One horizontal item: output pixels [xo0, xo1) of the 32 rows of group `grp`.
 // ---------------------------------------------------------------------------------------------------------
 template <int S, int STEP, int NCH, int EPI, int NCO>
-__device__ __forceinline__ void s3_h_item(const H2Params &p, const CUtensorMap *tmap, const CUtensorMap *tmap_u, unsigned char *wbase,
+__device__ __forceinline__ void s3_h_item(const H2Params &p, const CUtensorMap *tmap, const CUtensorMap *tmap_u, int *dbg, unsigned char *wbase,
                                           int ring_bytes, unsigned char *tab_s, const float *ord_s, int grp, int xo0, int xo1, bool uni,
-                                          bool first_item) {
+                                          unsigned &ph) {
   constexpr int SS = (S + 1) & ~1;
   constexpr int KP = iwb2_h_kp(STEP), NST = iwb2_h_nst(STEP);
   constexpr int TP = iwb2_tile_pitch(KP * NCH + 3);
@@ -332,7 +370,7 @@ __device__ __forceinline__ void s3_h_item(const H2Params &p, const CUtensorMap *
       s2_bulk_g2s(dst + 32 * TPU * 4, p.sc.w + (ptrdiff_t)(B0 + n * GU) * SS, GU * SS * 8, bar);
     }
   };
-  s3_reset_bars(bar0, lane, first_item);
+  __syncwarp();                                                 // (every lane is done with the previous item's ring and window table)
   s3_fence_proxy_all();                                         // the rows were written through the generic proxy (other SMs)
   if (uni) {
 #pragma unroll
@@ -439,8 +477,7 @@ __device__ __forceinline__ void s3_h_item(const H2Params &p, const CUtensorMap *
 
   if (STEP > 0 && uni) {
     int slot = 0;
-    unsigned par = 0;
-    s2_mbar_wait(bar0, 0);
+    s3_slot_wait(bar0, 0, ph, dbg, 5, grp, xo0);
     const unsigned rowoff = lane * (TPU * 4);
     float4 ch;
     auto lds128 = [](unsigned a) { float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v; };
@@ -451,13 +488,12 @@ __device__ __forceinline__ void s3_h_item(const H2Params &p, const CUtensorMap *
     for (int c = 0; c < NCH; c++) vc[c] = (double)elem(ch, c);
     for (int cyc = 0; cyc < ncyc; cyc++) {
       const int nslot = slot + 1 == NSTU ? 0 : slot + 1;
-      const unsigned npar = nslot == 0 ? par ^ 1 : par;
       const unsigned sb = ring0 + slot * STAGE_U + rowoff, sbn = ring0 + nslot * STAGE_U + rowoff;
       const unsigned wb = ring0 + slot * STAGE_U + 32 * TPU * 4;
       const int og = og0 + cyc * S;
 #pragma unroll
       for (int r = 0; r < GU; r++) {
-        if (r == GU - 1) s2_mbar_wait(bar0 + 8 * nslot, npar);
+        if (r == GU - 1) s3_slot_wait(bar0, nslot, ph, dbg, 6, grp, cyc);
         float nf[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
@@ -471,15 +507,13 @@ __device__ __forceinline__ void s3_h_item(const H2Params &p, const CUtensorMap *
       __syncwarp();
       if (cyc + NSTU <= ncyc) fill_u(cyc + NSTU, slot);
       slot = nslot;
-      par = npar;
     }
     flush(xo1);
     return;
   }
 
   int ld_stage = 0, ld_slot = 0, w_slot = 0;
-  unsigned parity = 0;
-  s2_mbar_wait(bar0, 0);
+  s3_slot_wait(bar0, 0, ph, dbg, 7, grp, xo0);
   const unsigned rowoff = lane * (TP * 4) + gskip * 4;
   unsigned pin = ring0 + rowoff;
   unsigned pin_end = pin + KP * NCH * 4;
@@ -489,8 +523,8 @@ __device__ __forceinline__ void s3_h_item(const H2Params &p, const CUtensorMap *
     __syncwarp();
     if (ld_stage >= 1 && ld_stage - 1 + NST < nstg) fill(ld_stage - 1 + NST, ld_slot == 0 ? NST - 1 : ld_slot - 1);
     ld_stage++;
-    if (++ld_slot == NST) { ld_slot = 0; parity ^= 1; }
-    if (ld_stage < nstg) s2_mbar_wait(bar0 + 8 * ld_slot, parity);
+    if (++ld_slot == NST) ld_slot = 0;
+    if (ld_stage < nstg) s3_slot_wait(bar0, ld_slot, ph, dbg, 8, grp, ld_stage);
     pin = ring0 + ld_slot * STAGE + rowoff;
     pin_end = pin + KP * NCH * 4;
   };
@@ -568,9 +602,10 @@ __global__ void __launch_bounds__(32 * IWB3_WARPS, 1)
   for (int i = threadIdx.x; i < 64; i += blockDim.x)
     ord_s[i] = ((float)iwb2_ord[(q.h.ch[0].dsubtype == 1 ? 64 : 0) + i] + 0.5f) / 64.0f;
   __syncthreads();
-  s2_mbar_wait(s2_addr(cbar), 0);
+  s3_mbar_wait(s2_addr(cbar), 0, q.sy.dbg, 10, 0, 0);
 
-  bool first_item = true;
+  unsigned ph = 0;                                              // phase bit of each pipeline slot of this warp
+  s3_init_bars(s2_addr(wbase + (is_v ? q.v_ring_bytes : q.h_ring_bytes + 32 * IWB2_OST_PITCH)), lane);
   if (is_v) {
     for (;;) {
       int it = 0;
@@ -581,8 +616,7 @@ __global__ void __launch_bounds__(32 * IWB3_WARPS, 1)
       int o0, o1;
       bool uni;
       s3_decode_part(q.v.part, q.n_gv, part, q.v.row_lo, q.v.row_hi, &o0, &o1, &uni);
-      s3_v_item<S, STEP, D16>(q.v, &vmap, &vmap_u, q.sy, wbase, q.v_ring_bytes, lut_s, wc, o0, o1, uni, first_item);
-      first_item = false;
+      s3_v_item<S, STEP, D16>(q.v, &vmap, &vmap_u, q.sy, wbase, q.v_ring_bytes, lut_s, wc, o0, o1, uni, ph);
     }
     return;
   }
@@ -609,16 +643,23 @@ __global__ void __launch_bounds__(32 * IWB3_WARPS, 1)
           const int want = q.sy.gen * rows * min(q.sy.cbw, q.nwc - b * q.sy.cbw);
           ok = s3_ld_acquire(cnt + b) >= want;
         }
-        while (!__all_sync(0xffffffffu, ok)) {
+        unsigned long long t0 = 0;
+        for (unsigned spins = 0; !__all_sync(0xffffffffu, ok); spins++) {
           __nanosleep(200);
+          int have = 0, want = 0;
           if (b <= bb) {
-            const int want = q.sy.gen * rows * min(q.sy.cbw, q.nwc - b * q.sy.cbw);
-            ok = s3_ld_acquire(cnt + b) >= want;
+            want = q.sy.gen * rows * min(q.sy.cbw, q.nwc - b * q.sy.cbw);
+            have = s3_ld_acquire(cnt + b);
+            ok = have >= want;
+          }
+          if ((spins & 255) == 255) {
+            const unsigned long long t = s3_now();
+            if (!t0) t0 = t;
+            else if (t - t0 > 4000000000ull && !ok) s3_die(q.sy.dbg, 9, grp, b, have, want);
           }
         }
       }
     }
-    s3_h_item<S, STEP, NCH, EPI, NCO>(q.h, &hmap, &hmap_u, wbase, q.h_ring_bytes, tab_s, ord_s, grp, xo0, xo1, uni, first_item);
-    first_item = false;
+    s3_h_item<S, STEP, NCH, EPI, NCO>(q.h, &hmap, &hmap_u, q.sy.dbg, wbase, q.h_ring_bytes, tab_s, ord_s, grp, xo0, xo1, uni, ph);
   }
 }

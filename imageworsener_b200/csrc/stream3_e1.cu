@@ -25,3 +25,41 @@ bool iwb3_run(const V2Job &vj, const H2Job &hj, VH3State *st, int nv_override, i
   if (launched) *launched = ok;
   return ok;
 }
+
+// ---- diagnostics of a launch that trapped (stream3_dev.cuh: s3_die) ----
+static int *g_dbg_host[64] = {nullptr};
+int *iwb3_debug_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!g_dbg_host[dev]) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!g_dbg_host[dev]) {
+      int *p = nullptr;
+      if (cudaHostAlloc((void **)&p, 160 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+      memset(p, 0, 160 * sizeof(int));
+      g_dbg_host[dev] = p;
+    }
+  }
+  return g_dbg_host[dev];                                       // (unified addressing: the host pointer is valid on the device)
+}
+std::string iwb3_debug_text() {
+  std::string out;
+  for (int dev = 0; dev < 64; dev++) {
+    int *p = g_dbg_host[dev];
+    if (!p || !p[0]) continue;
+    static const char *what[] = {"?", "V uniform first stage", "V uniform stage", "V general first stage", "V general stage", "H uniform first stage",
+                                 "H uniform stage", "H general first stage", "H general stage", "H group counter", "CTA tables"};
+    char line[256];
+    snprintf(line, sizeof line, "fused kernel: %d warp(s) gave up waiting on device %d;", p[0], dev);
+    out += line;
+    for (int k = 0; k < std::min(p[0], 15); k++) {
+      const int *r = p + 8 + 8 * k;
+      snprintf(line, sizeof line, " [%s: cta %d warp %d a=%d b=%d c=%d d=%d]", what[r[0] >= 0 && r[0] <= 10 ? r[0] : 0], r[1], r[2], r[3], r[4], r[5], r[6]);
+      out += line;
+    }
+    memset(p, 0, 160 * sizeof(int));
+  }
+  return out;
+}

@@ -344,6 +344,10 @@ void iwb200_job_set_profiling(iwb200_job *job, int on);
  * second generation (two kernels per chunk), 3 the fused persistent vertical + horizontal kernel; -1 for a null job.
  * Context option "cuda:gen" = 1 | 2 | 3 forces a generation where the job allows it (3: also for small launches). */
 int iwb200_job_last_kernel_generation(const iwb200_job *job);
+/* Diagnostics: every wait inside the fused kernel is bounded (seconds); a warp that gives up records what it waited for
+ * and the launch ends with an error instead of hanging the device.  Copies the record as text into buf (empty string
+ * if there is none), clears it, returns its length. */
+int iwb200_debug_fused_trap(char *buf, int buflen);
 int iwb200_job_kernel_stats(iwb200_job *job, int which, int *launches, double *total_ms);
 void iwb200_job_reset_stats(iwb200_job *job);
 
