@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -105,12 +106,20 @@ struct dev_guard {
   }
   ~dev_guard() { if (prev >= 0) cudaSetDevice(prev); }
 };
-// true exactly once per (call site tag, device): per-device kernel attributes
-static bool first_on_device(std::atomic<unsigned long long> &mask) {
+// Run `f` exactly once per (call site, device), and let nobody past this point before it has finished: kernel
+// attributes are per device, and contexts run concurrently from several threads (a launch that overtakes the attribute
+// call of another thread fails with "too much shared memory").
+static std::mutex g_once_mu;
+template <class F>
+static void once_per_device(std::atomic<unsigned long long> &mask, F f) {
   int dev = 0;
   cudaGetDevice(&dev);
   const unsigned long long bit = 1ull << (dev & 63);
-  return !(mask.fetch_or(bit) & bit);
+  if (mask.load(std::memory_order_acquire) & bit) return;
+  std::lock_guard<std::mutex> lk(g_once_mu);
+  if (mask.load(std::memory_order_relaxed) & bit) return;
+  f();
+  mask.fetch_or(bit, std::memory_order_release);
 }
 static bool dev_select(int device, std::string &err) {
   int count = 0;
@@ -265,7 +274,7 @@ struct iwb200_job {
 #if !defined(IWB_EMU)
   FastPlan fused;
   std::vector<std::unique_ptr<VH3State>> vh3;    // fused-kernel state per row range (stream3.cuh)
-  int gen3 = 1;                                 // 0: never, 1: when the launch is large enough, 2: whenever supported
+  int gen3 = 0;                                 // the fused kernel is opt-in (cuda:gen=3): 0 never, 2 whenever supported
   int gen3_nv = 0, gen3_seg = 0;
   struct s2_tables { Sched2 v, h; Quant2 q[4]; };
   std::unique_ptr<s2_tables> s2_store;
@@ -528,17 +537,17 @@ void launch_v(const VStreamParams &p, dim3 grid, size_t smem, iwb_stream st) {
   // the cp.async ring moves NC bytes per thread and row: needs NC in {4,8} and NC-byte aligned rows
   const bool ring = NC >= 4 && (p.bpr % NC == 0) && (((uintptr_t)p.src + p.x0_bytes) % NC == 0) && (p.ncols % NC == 0);
   static std::atomic<unsigned long long> attr{0};          // the attribute is per device
-  if (first_on_device(attr)) {
+  once_per_device(attr, [] {
     cudaFuncSetAttribute(iwb_vstream<S, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(iwb_vstream<S, NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  }
+  });
   if (ring) iwb_vstream<S, NC, true><<<grid, IWB_V_THREADS, smem, st>>>(p);
   else iwb_vstream<S, NC, false><<<grid, IWB_V_THREADS, smem, st>>>(p);
 }
 template <int S, int NCH, int R, int EPI>
 void launch_h(const HStreamParams &p, dim3 grid, size_t smem, iwb_stream st) {
   static std::atomic<unsigned long long> attr{0};
-  if (first_on_device(attr)) cudaFuncSetAttribute(iwb_hstream<S, NCH, R, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  once_per_device(attr, [] { cudaFuncSetAttribute(iwb_hstream<S, NCH, R, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
   iwb_hstream<S, NCH, R, EPI><<<grid, IWB_H_THREADS, smem, st>>>(p);
 }
 
@@ -871,7 +880,7 @@ static void fused_plan_build(iwb200_job *job, FastPlan *f) {
       if (const char *o2 = iwb_option(ctx, "cuda:seg2")) f->seg2 = std::max(4, atoi(o2) & ~3);
       if (const char *o2 = iwb_option(ctx, "cuda:uniform")) f->uniform = atoi(o2) != 0;
       if (const char *o2 = iwb_option(ctx, "cuda:overlap")) f->overlap = std::max(1, std::min(32, atoi(o2)));
-      if (const char *o2 = iwb_option(ctx, "cuda:gen")) { const int g = atoi(o2); job->gen3 = g == 3 ? 2 : (g == 2 ? 0 : 1); }
+      if (const char *o2 = iwb_option(ctx, "cuda:gen")) job->gen3 = atoi(o2) == 3 ? 2 : 0;
       if (const char *o2 = iwb_option(ctx, "cuda:nv")) job->gen3_nv = atoi(o2);
       if (const char *o2 = iwb_option(ctx, "cuda:seg3")) job->gen3_seg = std::max(16, atoi(o2) & ~3);
       if (rep && !f->same_tables) ok = false;                    // (one decision serves the three bytes unless the dither is random)
@@ -948,9 +957,9 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
       vj.S = f->SV; vj.first_host = f->vfirst.data(); vj.last_host = f->vlast.data(); vj.strip_override = f->strip2; vj.allow_uniform = f->uniform;
       job->last_path = 2; job->last_c0 = c0; job->last_c1 = c1; job->last_sh = hp.sh; job->last_pitch = pitch; job->last_inter = inter;
       if (nsub > 1 && i >= 2) cudaStreamWaitEvent(sv, (cudaEvent_t)f->ev[64 + i - 2], 0);   // this half was read by H(i-2)
-      // generation 3: both passes in one persistent kernel (stream3.cuh), when the launch is large enough to fill it
-      if (nsub == 1 && job->gen3 && iwb3_supported(f->SV, f->SH, nch, f->nco, f->epi, f->depth16) &&
-          (job->gen3 == 2 || ((long long)(c1 - c0) * vp.ncols >= (8ll << 20) && out.width >= 512))) {
+      // generation 3: both passes in one persistent kernel (stream3.cuh).  Opt-in: measured slower than the two
+      // kernels on cfg2 (0.33 ms against 0.20 ms)
+      if (nsub == 1 && job->gen3 && iwb3_supported(f->SV, f->SH, nch, f->nco, f->epi, f->depth16)) {
         VH3State *stt = nullptr;
         for (auto &u : job->vh3) if (u->c0 == c0 && u->c1 == c1) stt = u.get();
         if (!stt) {

@@ -22,11 +22,14 @@
 
 __device__ __forceinline__ void s3_mbar_inval(unsigned bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void s3_fence_proxy_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// (polling with a relaxed load and one acquire fence once the value is there: an acquire load costs a full L1
+// invalidation per poll)
 __device__ __forceinline__ int s3_ld_acquire(const int *p) {
   int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void s3_acquire_fence() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void s3_red_release(int *p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -102,9 +105,10 @@ __device__ __forceinline__ void s3_v_item(const V2Params &p, const CUtensorMap *
   constexpr int STAGE_U = (GU * TW + GU * SS * 8 + 127) & ~127;
   const int lane = threadIdx.x & 31;
   const int wcol0 = wc * 128;
-  const unsigned ring0 = s2_addr(wbase);
-  const unsigned bar0 = ring0 + ring_bytes;
-  int *last_s = (int *)(wbase + ring_bytes + 64);               // general path: [nout]
+  // a warp's region: [8 pipeline barriers, 128 bytes][ring][window table of the general path]
+  const unsigned bar0 = s2_addr(wbase);
+  const unsigned ring0 = bar0 + 128;
+  int *last_s = (int *)(wbase + 128 + ring_bytes);              // general path: [nout]
   const int col0 = wcol0 + lane * 4;
   const bool full = col0 + 4 <= p.ncols;
   if (STEP == 0) uni = false;
@@ -194,9 +198,9 @@ __device__ __forceinline__ void s3_v_item(const V2Params &p, const CUtensorMap *
   const ptrdiff_t out_step = p.pitch;
   int *cnt = sy.cnt + (wc / sy.cbw);                            // this warp column's counter of group 0
   int pending = 0;                                              // rows finished in the current group, not yet announced
-  auto finish = [&](int k, int o) {
+  // one finished intermediate row of this thread's 4 columns (already rounded to FP32, reference: src/imagew-main.c:905-912)
+  auto emit = [&](int o, float f0, float f1, float f2, float f3) {
     if (o >= o0 && o < o1) {
-      const float f0 = (float)acc[k][0], f1 = (float)acc[k][1], f2 = (float)acc[k][2], f3 = (float)acc[k][3];
       if (full) {
         if (sh == 0) {
           *reinterpret_cast<float4 *>(outp) = make_float4(f0, f1, f2, f3);
@@ -220,17 +224,26 @@ __device__ __forceinline__ void s3_v_item(const V2Params &p, const CUtensorMap *
       if ((rel & 31) == 31 || o == o1 - 1) {                    // the group (or the item) ends here: announce the rows
         __syncwarp();                                           // every lane's stores are ordered before lane 0's release
         if (lane == 0) {
-          __threadfence();
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
           s3_red_release(cnt + (ptrdiff_t)(rel >> 5) * sy.ncb, pending);
         }
         pending = 0;
       }
     }
+  };
+  auto finish = [&](int k, int o) {                             // (k is a compile-time constant at every call)
+    const float f0 = (float)acc[k][0], f1 = (float)acc[k][1], f2 = (float)acc[k][2], f3 = (float)acc[k][3];
 #pragma unroll
     for (int c = 0; c < 4; c++) acc[k][c] = 0.0;
+    emit(o, f0, f1, f2, f3);
   };
 
   if (STEP > 0 && uni) {
+    // One cycle = S outputs = S*STEP input rows = one stage.  The loop over the cycle's outputs is NOT unrolled: the
+    // tap code is the same for every output (all S slots take a tap from every row), only the slot that completes
+    // differs, and that is a small switch.  The body is ~1/S of the straight-line version of stream2_dev.cuh, so the
+    // vertical and the horizontal loop fit the instruction cache together (ncu on the unrolled version of this kernel:
+    // 2.6 warps stalled on instruction fetch per issue, against 0.07 / 0.24 in the separate kernels).
     int slot = 0;
     s3_slot_wait(bar0, 0, ph, sy.dbg, 1, wc, o0);
     double vc[4];
@@ -245,13 +258,30 @@ __device__ __forceinline__ void s3_v_item(const V2Params &p, const CUtensorMap *
       const unsigned sb = ring0 + slot * STAGE_U + lane * (TW / 32), sbn = ring0 + nslot * STAGE_U + lane * (TW / 32);
       const unsigned wb = ring0 + slot * STAGE_U + GU * TW;
       const int og = og0 + cyc * S;
+#pragma unroll 1
+      for (int k = 0; k < S; k++) {
 #pragma unroll
-      for (int r = 0; r < GU; r++) {
-        if (r == GU - 2) s3_slot_wait(bar0, nslot, ph, sy.dbg, 2, wc, cyc);
-        const word xcur = xn;
-        xn = ring_word(r + 2 < GU ? sb + (r + 2) * TW : sbn + (r + 2 - GU) * TW);
-        taps(vc, xcur, wb + r * SS * 8);
-        if ((r + 1) % STEPQ == 0) finish((r + 1) / STEPQ - 1, og + (r + 1) / STEPQ - 1);
+        for (int j = 0; j < STEPQ; j++) {
+          const int r = k * STEPQ + j;
+          if (r == GU - 2) s3_slot_wait(bar0, nslot, ph, sy.dbg, 2, wc, cyc);   // the last two rows prefetch from the next stage
+          const word xcur = xn;
+          xn = ring_word(r + 2 < GU ? sb + (r + 2) * TW : sbn + (r + 2 - GU) * TW);
+          taps(vc, xcur, wb + r * SS * 8);
+        }
+        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+        switch (k) {
+#define IWB3_VCASE(K)                                                                                   \
+  case K:                                                                                               \
+    if (K < S) {                                                                                        \
+      f0 = (float)acc[K < S ? K : 0][0]; f1 = (float)acc[K < S ? K : 0][1];                             \
+      f2 = (float)acc[K < S ? K : 0][2]; f3 = (float)acc[K < S ? K : 0][3];                             \
+      acc[K < S ? K : 0][0] = 0.0; acc[K < S ? K : 0][1] = 0.0; acc[K < S ? K : 0][2] = 0.0; acc[K < S ? K : 0][3] = 0.0; \
+    }                                                                                                   \
+    break;
+          IWB3_VCASE(0) IWB3_VCASE(1) IWB3_VCASE(2) IWB3_VCASE(3) IWB3_VCASE(4) IWB3_VCASE(5) IWB3_VCASE(6) IWB3_VCASE(7)
+#undef IWB3_VCASE
+        }
+        emit(og + k, f0, f1, f2, f3);
       }
       __syncwarp();
       if (cyc + NSTU <= ncyc) fill_u(cyc + NSTU, slot);
@@ -332,10 +362,11 @@ __device__ __forceinline__ void s3_h_item(const H2Params &p, const CUtensorMap *
   const int lane = threadIdx.x & 31;
   if (STEP == 0) uni = false;
 
-  unsigned char *ost = wbase + ring_bytes;
-  const unsigned ring0 = s2_addr(wbase);
-  const unsigned bar0 = s2_addr(wbase + ring_bytes + 32 * IWB2_OST_PITCH);
-  int *last_s = (int *)(wbase + ring_bytes + 32 * IWB2_OST_PITCH + 64);
+  // a warp's region: [8 pipeline barriers, 128 bytes][ring][output staging][window table of the general path]
+  unsigned char *ost = wbase + 128 + ring_bytes;
+  const unsigned bar0 = s2_addr(wbase);
+  const unsigned ring0 = bar0 + 128;
+  int *last_s = (int *)(wbase + 128 + ring_bytes + 32 * IWB2_OST_PITCH);
 
   const int jb = p.row_lo + grp * 32;
   const int y = jb + lane;
@@ -431,7 +462,8 @@ __device__ __forceinline__ void s3_h_item(const H2Params &p, const CUtensorMap *
              (upto - staged_from) * NCO, min(32, p.row_hi - jb), walign, lane);
     staged_from = upto;
   };
-  auto finish = [&](int k, int xo) {
+  // one finished output pixel: the resampled linear samples of its channels -> quantise + dither -> staged bytes
+  auto emit = [&](int xo, const double (&sv)[NCH]) {
     if (xo >= xo0 && xo < xo1) {
       if (xo - staged_from >= FU) flush(xo);
       const unsigned dstb = ost_a + (xo - staged_from) * NCO;
@@ -453,7 +485,7 @@ __device__ __forceinline__ void s3_h_item(const H2Params &p, const CUtensorMap *
           rng[c] = iwb_prng_step(rng[c]);
           t[c] = (float)draw[c] * (1.0f / 4294967295.0f);
         }
-        code[c] = quantise8_try<EPI>(tab_c[c], qmargin[c], qtop[c], t[c], acc[k][ci], &sure[c], &qg[c]);
+        code[c] = quantise8_try<EPI>(tab_c[c], qmargin[c], qtop[c], t[c], sv[ci], &sure[c], &qg[c]);
         all_sure = all_sure && sure[c];
       }
       if (__any_sync(0xffffffffu, !all_sure)) {
@@ -464,18 +496,28 @@ __device__ __forceinline__ void s3_h_item(const H2Params &p, const CUtensorMap *
           if (!sure[c]) {
             const int tb = p.same_tables ? 0 : c;
             code[c] = exact8_v2<EPI == 1 ? 0 : (EPI == 2 ? 4 : (EPI == 3 ? 1 : 3))>((const double *)(tab_s + (size_t)tb * IWB2_TAB_BYTES + IWB2_TAB_THR),
-                                                                 p.q[tb].top, acc[k][ci], qg[c], t[c], draw[c]);
+                                                                 p.q[tb].top, sv[ci], qg[c], t[c], draw[c]);
           }
         }
       }
 #pragma unroll
       for (int c = 0; c < NCO; c++) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dstb + c), "r"(code[c]) : "memory");
     }
+  };
+  auto finish = [&](int k, int xo) {                            // (k is a compile-time constant at every call)
+    double sv[NCH];
 #pragma unroll
-    for (int c = 0; c < NCH; c++) acc[k][c] = 0.0;
+    for (int c = 0; c < NCH; c++) { sv[c] = acc[k][c]; acc[k][c] = 0.0; }
+    emit(xo, sv);
   };
 
   if (STEP > 0 && uni) {
+    // The loop over a cycle's outputs is rolled, U outputs per iteration (U = the smallest count whose samples fill whole
+    // 16-byte chunks of the tile row, so that the position of a sample within its chunk stays a compile-time constant):
+    // the tap code does not depend on which slot completes, the epilogue exists U times instead of S times (see the
+    // vertical item for why).
+    constexpr int U = (STEPQ * NCH) % 4 == 0 ? 1 : ((2 * STEPQ * NCH) % 4 == 0 ? 2 : 4);
+    static_assert(STEP == 0 || S % U == 0, "a cycle must be a whole number of loop iterations");
     int slot = 0;
     s3_slot_wait(bar0, 0, ph, dbg, 5, grp, xo0);
     const unsigned rowoff = lane * (TPU * 4);
@@ -491,18 +533,44 @@ __device__ __forceinline__ void s3_h_item(const H2Params &p, const CUtensorMap *
       const unsigned sb = ring0 + slot * STAGE_U + rowoff, sbn = ring0 + nslot * STAGE_U + rowoff;
       const unsigned wb = ring0 + slot * STAGE_U + 32 * TPU * 4;
       const int og = og0 + cyc * S;
+#pragma unroll 1
+      for (int kk = 0; kk < S / U; kk++) {
+        double sv[U][NCH];
 #pragma unroll
-      for (int r = 0; r < GU; r++) {
-        if (r == GU - 1) s3_slot_wait(bar0, nslot, ph, dbg, 6, grp, cyc);
-        float nf[NCH];
+        for (int u = 0; u < U; u++) {
 #pragma unroll
-        for (int c = 0; c < NCH; c++) {
-          const int f = (r + 1 < GU ? (r + 1) * NCH : 0) + c;
-          if (f % 4 == 0) ch = lds128((r + 1 < GU ? sb : sbn) + f * 4);
-          nf[c] = elem(ch, f % 4);
+          for (int j = 0; j < STEPQ; j++) {
+            const int r = (kk * U + u) * STEPQ + j;             // pixel column of the stage being consumed
+            if (r == GU - 1) s3_slot_wait(bar0, nslot, ph, dbg, 6, grp, cyc);   // the last column prefetches from the next stage
+            float nf[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+              // flat index of the next column's sample within its stage: ((r + 1) mod GU) * NCH + c; its position in
+              // the 16-byte chunk only depends on u, j, c (kk * U * STEP * NCH is a multiple of 4)
+              constexpr int dummy = 0; (void)dummy;
+              const int fpos = ((u * STEPQ + j + 1) * NCH + c) % 4;
+              const int f = (r + 1 < GU ? (r + 1) * NCH : 0) + c;
+              if (fpos == 0) ch = lds128((r + 1 < GU ? sb : sbn) + f * 4);
+              nf[c] = elem(ch, fpos);
+            }
+            taps(vc, nf, wb + r * SS * 8);
+          }
+          // slot kk*U + u is complete
+          switch (kk) {
+#define IWB3_HCASE(K)                                                                                  \
+  case K:                                                                                              \
+    if (K * U + u < S) {                                                                               \
+      _Pragma("unroll") for (int c = 0; c < NCH; c++) {                                                \
+        sv[u][c] = acc[K * U + u < S ? K * U + u : 0][c];                                              \
+        acc[K * U + u < S ? K * U + u : 0][c] = 0.0;                                                   \
+      }                                                                                                \
+    }                                                                                                  \
+    break;
+            IWB3_HCASE(0) IWB3_HCASE(1) IWB3_HCASE(2) IWB3_HCASE(3) IWB3_HCASE(4) IWB3_HCASE(5) IWB3_HCASE(6) IWB3_HCASE(7)
+#undef IWB3_HCASE
+          }
+          emit(og + kk * U + u, sv[u]);
         }
-        taps(vc, nf, wb + r * SS * 8);
-        if ((r + 1) % STEPQ == 0) finish((r + 1) / STEPQ - 1, og + (r + 1) / STEPQ - 1);
       }
       __syncwarp();
       if (cyc + NSTU <= ncyc) fill_u(cyc + NSTU, slot);
@@ -585,6 +653,7 @@ __global__ void __launch_bounds__(32 * IWB3_WARPS, 1)
   float *ord_s = (float *)(tab_s + (size_t)ntab * IWB2_TAB_BYTES);
   uint64_t *cbar = (uint64_t *)(ord_s + 64);
   unsigned char *warps0 = (unsigned char *)(cbar + 16);         // 128 bytes of CTA barriers keep the warp regions on 128-byte boundaries
+  // warps [0, nv) are vertical, the rest horizontal, each with a shared-memory region of its kind
   const bool is_v = warp < q.nv;
   unsigned char *wbase = is_v ? warps0 + (size_t)warp * q.v_warp_bytes
                               : warps0 + (size_t)q.nv * q.v_warp_bytes + (size_t)(warp - q.nv) * q.h_warp_bytes;
@@ -605,61 +674,76 @@ __global__ void __launch_bounds__(32 * IWB3_WARPS, 1)
   s3_mbar_wait(s2_addr(cbar), 0, q.sy.dbg, 10, 0, 0);
 
   unsigned ph = 0;                                              // phase bit of each pipeline slot of this warp
-  s3_init_bars(s2_addr(wbase + (is_v ? q.v_ring_bytes : q.h_ring_bytes + 32 * IWB2_OST_PITCH)), lane);
+  s3_init_bars(s2_addr(wbase), lane);
+
+  auto run_v = [&](int it) {
+    const int part = it / q.nwc, wc = it - part * q.nwc;
+    int o0, o1;
+    bool uni;
+    s3_decode_part(q.v.part, q.n_gv, part, q.v.row_lo, q.v.row_hi, &o0, &o1, &uni);
+    s3_v_item<S, STEP, D16>(q.v, &vmap, &vmap_u, q.sy, wbase, q.v_ring_bytes, lut_s, wc, o0, o1, uni, ph);
+  };
+  struct hitem { int grp, xo0, xo1; bool uni; };
+  auto h_decode = [&](int it) {
+    hitem h;
+    const int gi = it / q.nparts_h, xp = it - gi * q.nparts_h;
+    h.grp = q.h_order[gi];
+    s3_decode_part(q.h.part, q.n_gh, xp, 0, q.h.out_w, &h.xo0, &h.xo1, &h.uni);
+    return h;
+  };
+  // Have the vertical items announced every row of the group in the columns this segment reads?  One counter per block
+  // of warp columns, target = launch number x rows of the group x warp columns of the block (see VH3Sync).  Warp-uniform
+  // result; `have` / `want` / `blk` describe a block that is still short (diagnostics).
+  auto h_ready = [&](const hitem &h, int *blk, int *have, int *want) {
+    const int ca = (q.h.sc.first[h.xo0] * NCH) / 128, cb = (q.h.sc.last[h.xo1 - 1] * NCH + NCH - 1) / 128;
+    const int ba = ca / q.sy.cbw, bb = min(cb / q.sy.cbw, q.sy.ncb - 1);
+    const int rows = min(32, q.h.row_hi - q.h.row_lo - h.grp * 32);
+    const int *cnt = q.sy.cnt + (ptrdiff_t)h.grp * q.sy.ncb;
+    bool ok = true;
+    for (int b = ba + lane; b - lane <= bb; b += 32) {
+      if (b <= bb) {
+        const int w = q.sy.gen * rows * min(q.sy.cbw, q.nwc - b * q.sy.cbw);
+        const int v = s3_ld_acquire(cnt + b);
+        if (v < w) { ok = false; *blk = b; *have = v; *want = w; }
+      }
+    }
+    return __all_sync(0xffffffffu, ok) != 0;
+  };
+  auto run_h = [&](const hitem &h) {
+    s3_acquire_fence();
+    s3_h_item<S, STEP, NCH, EPI, NCO>(q.h, &hmap, &hmap_u, q.sy.dbg, wbase, q.h_ring_bytes, tab_s, ord_s, h.grp, h.xo0, h.xo1, h.uni, ph);
+  };
+  auto wait_h = [&](const hitem &h) {
+    int blk = 0, have = 0, want = 0;
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0; !h_ready(h, &blk, &have, &want); spins++) {
+      __nanosleep(500);
+      if ((spins & 255) == 255) {
+        const unsigned long long t = s3_now();
+        if (!t0) t0 = t;
+        else if (t - t0 > 4000000000ull) s3_die(q.sy.dbg, 9, h.grp, blk, have, want);
+      }
+    }
+  };
+  auto pop = [&](int *head, int base) {                         // one ticket (warp-uniform)
+    int it = 0;
+    if (lane == 0) it = atomicAdd(head, 1) - base;
+    return __shfl_sync(0xffffffffu, it, 0);
+  };
+
   if (is_v) {
     for (;;) {
-      int it = 0;
-      if (lane == 0) it = atomicAdd(q.sy.v_head, 1) - q.sy.v_base;
-      it = __shfl_sync(0xffffffffu, it, 0);
+      const int it = pop(q.sy.v_head, q.sy.v_base);
       if (it >= q.n_vitems) break;
-      const int part = it / q.nwc, wc = it - part * q.nwc;
-      int o0, o1;
-      bool uni;
-      s3_decode_part(q.v.part, q.n_gv, part, q.v.row_lo, q.v.row_hi, &o0, &o1, &uni);
-      s3_v_item<S, STEP, D16>(q.v, &vmap, &vmap_u, q.sy, wbase, q.v_ring_bytes, lut_s, wc, o0, o1, uni, ph);
+      run_v(it);
     }
     return;
   }
   for (;;) {
-    int it = 0;
-    if (lane == 0) it = atomicAdd(q.sy.h_head, 1) - q.sy.h_base;
-    it = __shfl_sync(0xffffffffu, it, 0);
+    const int it = pop(q.sy.h_head, q.sy.h_base);
     if (it >= q.n_hitems) break;
-    const int gi = it / q.nparts_h, xp = it - gi * q.nparts_h;
-    const int grp = q.h_order[gi];
-    int xo0, xo1;
-    bool uni;
-    s3_decode_part(q.h.part, q.n_gh, xp, 0, q.h.out_w, &xo0, &xo1, &uni);
-    // wait for the vertical items that produce the columns this segment reads in this group: one counter per block of
-    // warp columns, target = launch number x rows of the group x warp columns of the block (see VH3Sync)
-    {
-      const int ca = (q.h.sc.first[xo0] * NCH) / 128, cb = (q.h.sc.last[xo1 - 1] * NCH + NCH - 1) / 128;
-      const int ba = ca / q.sy.cbw, bb = min(cb / q.sy.cbw, q.sy.ncb - 1);
-      const int rows = min(32, q.h.row_hi - q.h.row_lo - grp * 32);
-      const int *cnt = q.sy.cnt + (ptrdiff_t)grp * q.sy.ncb;
-      for (int b = ba + lane; b - lane <= bb; b += 32) {
-        bool ok = true;
-        if (b <= bb) {
-          const int want = q.sy.gen * rows * min(q.sy.cbw, q.nwc - b * q.sy.cbw);
-          ok = s3_ld_acquire(cnt + b) >= want;
-        }
-        unsigned long long t0 = 0;
-        for (unsigned spins = 0; !__all_sync(0xffffffffu, ok); spins++) {
-          __nanosleep(200);
-          int have = 0, want = 0;
-          if (b <= bb) {
-            want = q.sy.gen * rows * min(q.sy.cbw, q.nwc - b * q.sy.cbw);
-            have = s3_ld_acquire(cnt + b);
-            ok = have >= want;
-          }
-          if ((spins & 255) == 255) {
-            const unsigned long long t = s3_now();
-            if (!t0) t0 = t;
-            else if (t - t0 > 4000000000ull && !ok) s3_die(q.sy.dbg, 9, grp, b, have, want);
-          }
-        }
-      }
-    }
-    s3_h_item<S, STEP, NCH, EPI, NCO>(q.h, &hmap, &hmap_u, q.sy.dbg, wbase, q.h_ring_bytes, tab_s, ord_s, grp, xo0, xo1, uni, ph);
+    const hitem h = h_decode(it);
+    wait_h(h);
+    run_h(h);
   }
 }

@@ -73,7 +73,7 @@ def test_malformed_device_lists_fail_loudly(prod, bad):
 
 @pytest.mark.gpu
 def test_unknown_device_ordinal_fails_loudly(prod):
-    cfg = configs.Config("bad", 64, 64, RGB, 8, 32, 32, "-width 32 -height 32")
+    cfg = configs.Config("bad", 256, 256, RGB, 8, 128, 128, "-width 128 -height 128")
     rows = configs.synth_rows(prod, cfg)
     with pytest.raises(L.IwError, match="device"):
         configs.run_host(prod, cfg, rows, options={"cuda:devices": "0,512"})
