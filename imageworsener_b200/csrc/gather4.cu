@@ -1,0 +1,127 @@
+// gather4.cu -- gather-form streaming kernels: instantiations, tensor maps, launch (design: gather4.cuh).
+#include "gather4_dev.cuh"
+#include "stream2_host.cuh"
+
+namespace {
+
+bool g4_input_map(const GVParams &p, bool d16, CUtensorMap *tm) {
+  const int bpc = d16 ? 2 : 1;
+  iwb2_encode_fn enc = iwb2_tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)p.ncols * bpc, (cuuint64_t)p.tm_rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)p.bpr};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 * bpc), (cuuint32_t)IWG_V_G};
+  const cuuint32_t estr[2] = {1, 1};
+  const void *base = p.src + (size_t)p.tm_row0 * p.bpr;
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool g4_inter_map(const GHParams &p, int box_cols, CUtensorMap *tm) {
+  iwb2_encode_fn enc = iwb2_tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)p.ncols, (cuuint64_t)(p.row_hi - p.row_lo)};
+  const cuuint64_t gstride[1] = {(cuuint64_t)p.pitch * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p.inter), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int W, bool D16, int NCHP>
+bool run_v(const GVJob &job, cudaStream_t st) {
+  GVParams p = job.p;
+  const int threads = 32 * IWG_WARPS;
+  const int colblocks = (p.ncols + 128 * IWG_WARPS - 1) / (128 * IWG_WARPS);
+  // strips: enough CTAs for ~2 waves at 4 CTAs per SM, but at least 64 output rows (a strip re-reads W input rows)
+  const int rows = p.row_hi - p.row_lo;
+  const int want = std::max(1, (8 * iwb2_sm_count()) / colblocks);
+  int strip = std::max(64, (rows + want - 1) / want);
+  strip = std::min(strip, 2048);
+  p.strip = strip;
+  const size_t tw = D16 ? 256 : 128;
+  const size_t smem = (D16 ? 0 : 2 * 256 * 8) + (size_t)IWG_WARPS * (IWG_V_NST * IWG_V_G * tw + 128) + (size_t)strip * 4 + 16;
+  CUtensorMap tm;
+  if (!g4_input_map(p, D16, &tm)) return false;
+  auto kernel = iwg_v<W, D16, NCHP>;
+  iwb2_ctas_per_sm(kernel, threads, smem);
+  kernel<<<dim3((unsigned)colblocks, (unsigned)((rows + strip - 1) / strip)), threads, smem, st>>>(tm, p);
+  return true;
+}
+
+template <int W, int NCH, int NCO, bool FAST>
+bool run_h(const GHJob &job, cudaStream_t st) {
+  GHParams p = job.p;
+  const int threads = 32 * IWG_WARPS;
+  const int groups = (p.row_hi - p.row_lo + 31) / 32;
+  const int rowblocks = (groups + IWG_WARPS - 1) / IWG_WARPS;
+  const int want = std::max(1, (8 * iwb2_sm_count()) / rowblocks);
+  int seg = std::max(64, (p.out_w + want - 1) / want);
+  seg = std::min((seg + 3) & ~3, 4096);
+  p.seg = seg;
+  constexpr int TP = iwb2_tile_pitch(IWG_H_KP * NCH + 3);
+  const size_t stage = ((size_t)32 * TP * 4 + 127) & ~(size_t)127;
+  const size_t smem = (size_t)IWG_WARPS * (IWG_H_NST * stage + 32 * IWG_OST_PITCH + 128) + (size_t)seg * 4 + 16;
+  CUtensorMap tm;
+  if (!g4_inter_map(p, TP, &tm)) return false;
+  auto kernel = iwg_h<W, NCH, NCO, FAST>;
+  iwb2_ctas_per_sm(kernel, threads, smem);
+  kernel<<<dim3((unsigned)((p.out_w + seg - 1) / seg), (unsigned)rowblocks), threads, smem, st>>>(tm, p);
+  return true;
+}
+
+template <int W>
+bool run_v_w(const GVJob &job, cudaStream_t st) {
+  if (job.p.depth16) return job.nchp == 4 ? run_v<W, true, 4>(job, st) : run_v<W, true, 2>(job, st);
+  return job.nchp == 4 ? run_v<W, false, 4>(job, st) : run_v<W, false, 2>(job, st);
+}
+// the straight-line epilogue's assumptions (gather4_dev.cuh: FAST)
+bool fast_epilogue(const GHJob &job) {
+  const GHParams &p = job.p;
+  if (job.nco != job.nch - 1 || p.cm.checker || p.cm.intclamp || p.out.is_float) return false;
+  for (int k = 0; k < job.nco; k++) {
+    const DevChanOut &o = p.ch[k];
+    if (!(o.qmode == 1 && !o.use_nc && !o.codeval && o.guess_cs >= 0 && o.ntab - 1 >= 8)) return false;
+    if (o.dfamily != 0 && o.dfamily != 1 && o.dfamily != 3) return false;
+    if (!o.premult || o.bkgd_translucent || o.is_alpha) return false;
+    if (o.ntab != p.ch[0].ntab || o.guess_cs != p.ch[0].guess_cs || o.guess_gamma != p.ch[0].guess_gamma || o.dfamily != p.ch[0].dfamily ||
+        o.dsubtype != p.ch[0].dsubtype || o.late_bkgd != p.ch[0].late_bkgd) return false;
+  }
+  return true;
+}
+template <int W>
+bool run_h_w(const GHJob &job, cudaStream_t st) {
+  const bool fast = fast_epilogue(job);
+  if (job.nch == 4) {
+    if (job.nco == 4) return run_h<W, 4, 4, false>(job, st);
+    if (job.nco == 3) return fast ? run_h<W, 4, 3, true>(job, st) : run_h<W, 4, 3, false>(job, st);
+    return false;
+  }
+  if (job.nco == 2) return run_h<W, 2, 2, false>(job, st);
+  if (job.nco == 1) return fast ? run_h<W, 2, 1, true>(job, st) : run_h<W, 2, 1, false>(job, st);
+  return false;
+}
+
+}  // namespace
+
+bool iwg_supported(int WV, int WH, int nch) {
+  auto okw = [](int w) { return w == 2 || w == 4 || w == 6 || w == 8; };
+  return okw(WV) && okw(WH) && (nch == 2 || nch == 4) && iwb2_tensor_map_encoder() != nullptr;
+}
+bool iwg_run_v(const GVJob &job, cudaStream_t st) {
+  switch (job.W) {
+    case 2: return run_v_w<2>(job, st);
+    case 4: return run_v_w<4>(job, st);
+    case 6: return run_v_w<6>(job, st);
+    case 8: return run_v_w<8>(job, st);
+  }
+  return false;
+}
+bool iwg_run_h(const GHJob &job, cudaStream_t st) {
+  switch (job.W) {
+    case 2: return run_h_w<2>(job, st);
+    case 4: return run_h_w<4>(job, st);
+    case 6: return run_h_w<6>(job, st);
+    case 8: return run_h_w<8>(job, st);
+  }
+  return false;
+}

@@ -386,16 +386,16 @@ IWB_HD void store_float(const DevOutput &out, int x, int y, int ch, double s) {
   p[0] = u.b[0]; p[1] = u.b[1]; p[2] = u.b[2]; p[3] = u.b[3];
 }
 
-// Compositing that happens after the horizontal pass (reference: src/imagew-main.c:1080-1115)
-IWB_HD double composite(const DevCommon &cm, const DevChanOut &o, double s, const float *final_alpha,
-                        int out_w, int x, int y) {
+// Compositing that happens after the horizontal pass (reference: src/imagew-main.c:1080-1115).  `a` is the resized
+// alpha of the pixel, already rounded to FP32 as the reference's final_alpha32 plane holds it (:1057-1061); it is only
+// read for channels that were premultiplied.
+IWB_HD double composite_a(const DevCommon &cm, const DevChanOut &o, double s, double a, int x, int y) {
   int alt = 0;
   if (cm.checker)
     alt = (((cm.check_ox + x) / cm.check_size) % 2) != (((cm.check_oy + y) / cm.check_size) % 2);
   double ba = 0.0;
   if (o.bkgd_translucent) ba = alt ? cm.bkgd2alpha : cm.bkgd1alpha;
   if (o.premult) {
-    double a = (double)final_alpha[(size_t)y * out_w + x];
     if (a != 0.0) s = xdiv(s, a);
     if (o.late_bkgd) {
       double bk = alt ? o.bkgd2 : o.bkgd1;
@@ -406,6 +406,11 @@ IWB_HD double composite(const DevCommon &cm, const DevChanOut &o, double s, cons
     s = xadd(s, xmul(ba, xsub(1.0, s)));
   }
   return s;
+}
+IWB_HD double composite(const DevCommon &cm, const DevChanOut &o, double s, const float *final_alpha,
+                        int out_w, int x, int y) {
+  const double a = o.premult ? (double)final_alpha[(size_t)y * out_w + x] : 0.0;
+  return composite_a(cm, o, s, a, x, y);
 }
 
 // Quantise + none/ordered/random dither (error diffusion has its own kernel).  `draw` is this sample's PRNG

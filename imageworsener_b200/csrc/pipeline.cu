@@ -24,6 +24,7 @@
 #include "fused.cuh"
 #include "stream2.cuh"
 #include "stream3.cuh"
+#include "gather4.cuh"
 #endif
 
 // ------------------------------------------------------------------------------------------------------
@@ -273,6 +274,21 @@ struct iwb200_job {
   void *d_out = nullptr; size_t d_out_bytes = 0;
 #if !defined(IWB_EMU)
   FastPlan fused;
+  // gather-form streaming kernels for images with alpha (gather4.cuh)
+  struct gather_plan {
+    int enabled = 0;
+    int WV = 0, WH = 0, nch = 0, depth16 = 0;
+    GSched sv{}, sh{};
+    std::vector<int> vfirst, vlast;               // host copies (band planning)
+    const double *lut_c = nullptr, *lut_a = nullptr;
+    DevChanOut ch[4];
+    const DevChanOut *ch_g = nullptr;             // ch[] in device memory
+    int nco = 0, out_src[4] = {0, 0, 0, 0};
+    int chan_of_proc[4] = {0, 0, 0, 0};           // interleaved channel of processed channel p
+    float *inter = nullptr;
+    int chunk_rows = 0;
+    size_t pitch = 0;
+  } gather;
   std::vector<std::unique_ptr<VH3State>> vh3;    // fused-kernel state per row range (stream3.cuh)
   int gen3 = 0;                                 // the fused kernel is opt-in (cuda:gen=3): 0 never, 2 whenever supported
   int gen3_nv = 0, gen3_seg = 0;
@@ -470,7 +486,10 @@ struct HostSched {
 // filter at |x| = 1 for odd integer reduction factors).  The schedule gives such an input the weight 0.0, as it
 // does for every input outside a slot's window, which leaves the sum bit-identical: an accumulator starts at +0.0
 // and a sum of two doubles is -0.0 only if both are, so it never holds -0.0, and x + (+-0.0) = x for any other x.
-bool build_sched(const iwb_axis_table &t, int max_slots, HostSched *hs) {
+// The windows of a tap list: [first[o], last[o]] for every output, widened (with zero weights) until starts and ends
+// are monotone.  false: the list does not qualify (virtual samples, repeated or decreasing sources, real breaks of
+// monotonicity).
+bool build_windows(const iwb_axis_table &t, HostSched *hs) {
   if (t.mode != 0 || t.n_out < 1) return false;
   const int n_in = t.n_in, n_out = t.n_out;
   hs->first.resize(n_out);
@@ -495,6 +514,12 @@ bool build_sched(const iwb_axis_table &t, int max_slots, HostSched *hs) {
     if (hs->last[o] < hs->last[o - 1] - 1) return false;
     hs->last[o] = std::max(hs->last[o], hs->last[o - 1]);
   }
+  return true;
+}
+
+bool build_sched(const iwb_axis_table &t, int max_slots, HostSched *hs) {
+  if (!build_windows(t, hs)) return false;
+  const int n_in = t.n_in, n_out = t.n_out;
   // most windows open at once
   int S = 1;
   for (int o = 0, lo = 0; o < n_out; o++) {
@@ -1061,6 +1086,153 @@ static bool fused_run(iwb200_job *job, FastPlan *f, const DevInput &in, const De
   if (cudaGetLastError() != cudaSuccess) return fail(job, "fast path: kernel launch failed");
   return true;
 }
+// ---- gather-form streaming kernels (gather4.cuh): jobs with a real alpha channel -------------------------------------
+// Per-output schedule: the window [first[o], first[o] + W) and its W weights (0.0 where the reference's list has no tap).
+static bool build_gather_sched(iwb200_job *job, const HostSched &hs, const iwb_axis_table &t, int W, GSched *d) {
+  const int n_out = t.n_out;
+  std::vector<double> w((size_t)n_out * W, 0.0);
+  for (int o = 0; o < n_out; o++)
+    for (int k = t.first[o]; k < t.first[o + 1]; k++) {
+      const int rel = t.src[k] - hs.first[o];
+      if (rel < 0 || rel >= W) return false;
+      w[(size_t)o * W + rel] = t.w[k];
+    }
+  d->first = job->upload(hs.first.data(), hs.first.size());
+  d->w = job->upload(w.data(), w.size());
+  d->n_in = t.n_in; d->n_out = n_out;
+  return d->first && d->w;
+}
+
+static void gather_plan_build(iwb200_job *job) {
+  iw_context *ctx = job->ctx;
+  iwb200_job::gather_plan &g = job->gather;
+  g.enabled = 0;
+  const int nch = ctx->in_nch_phys;
+  if (ctx->img1.sampletype != IW_SAMPLETYPE_UINT || (ctx->img1.bit_depth != 8 && ctx->img1.bit_depth != 16)) return;
+  if ((ctx->img1.orient_transform & 7) != 0) return;
+  if (nch != 2 && nch != 4) return;
+  if (ctx->in_type_logical != ctx->img1.imgtype || !job->has_alpha || job->nproc != nch || ctx->mid_nch != nch) return;
+  if (ctx->in_alpha_index != nch - 1) return;
+  if (ctx->img2.sampletype != IW_SAMPLETYPE_UINT || (ctx->img2.bit_depth != 8 && ctx->img2.bit_depth != 16)) return;
+  if (job->any_errdiff) return;
+  if (ctx->axis[0].per_channel_tables || ctx->axis[1].per_channel_tables) return;
+  // processed channel p <-> interleaved (physical) channel: a bijection; colour premultiplied, alpha plain
+  bool seen[4] = {false, false, false, false};
+  const double *lut_c = nullptr, *lut_a = nullptr;
+  for (int p = 0; p < job->nproc; p++) {
+    const iwb_mid_channel &mc = ctx->mid_ci[job->mid_index[p]];
+    const int c = mc.in_channel;
+    if (c < 0 || c >= nch || seen[c] || mc.to_gray) return;
+    seen[c] = true;
+    const bool is_alpha = mc.channeltype == IW_CHANNELTYPE_ALPHA;
+    if (is_alpha != (c == nch - 1)) return;
+    const DevChanIn &ci = job->cin[p];
+    if (ci.early_bkgd || !ci.lut[0]) return;
+    if (is_alpha) {
+      if (ci.premult) return;
+      if (lut_a && lut_a != ci.lut[0]) return;
+      lut_a = ci.lut[0];
+    } else {
+      if (!ci.premult || !ci.alpha_lut || ci.alpha_ch != nch - 1) return;
+      if ((lut_c && lut_c != ci.lut[0]) || (lut_a && lut_a != ci.alpha_lut)) return;
+      lut_c = ci.lut[0];
+      lut_a = ci.alpha_lut;
+    }
+    g.chan_of_proc[p] = c;
+    g.ch[c] = job->cout[p];
+  }
+  if (!lut_c || !lut_a) return;
+  HostSched hv, hh;
+  if (!build_windows(job->vtab[0], &hv) || !build_windows(job->htab[0], &hh)) return;
+  auto width_of = [](const HostSched &h) {
+    int m = 1;
+    for (size_t o = 0; o < h.first.size(); o++) m = std::max(m, h.last[o] - h.first[o] + 1);
+    return (m + 1) & ~1;
+  };
+  g.WV = width_of(hv); g.WH = width_of(hh);
+  if (!iwg_supported(g.WV, g.WH, nch)) return;
+  g.nco = ctx->out_nch;
+  for (int k = 0; k < g.nco; k++) {
+    int src = -1;
+    for (int c = 0; c < nch; c++) if (g.ch[c].out_ch == k) src = c;
+    if (src != k) return;                                        // (output channel k is interleaved channel k)
+    g.out_src[k] = src;
+  }
+  if (g.nco != nch && g.nco != nch - 1) return;
+  if (!build_gather_sched(job, hv, job->vtab[0], g.WV, &g.sv) || !build_gather_sched(job, hh, job->htab[0], g.WH, &g.sh)) return;
+  {
+    DevChanOut four[4];
+    for (int c = 0; c < 4; c++) four[c] = g.ch[c < nch ? c : 0];
+    g.ch_g = job->upload(four, 4);
+    if (!g.ch_g) return;
+  }
+  g.vfirst = hv.first; g.vlast = hv.last;
+  g.lut_c = lut_c; g.lut_a = lut_a;
+  g.nch = nch;
+  g.depth16 = ctx->img1.bit_depth == 16;
+  const int ncols = job->in_w * nch;
+  g.pitch = (size_t)((ncols + 3) & ~3);
+  size_t rows = ((size_t)512 << 20) / (g.pitch * 4);
+  rows = std::max<size_t>(32, (rows / 32) * 32);
+  rows = std::min<size_t>(rows, (size_t)((job->out.height + 31) / 32) * 32);
+  g.chunk_rows = (int)rows;
+  g.enabled = 1;
+}
+
+static bool gather_run(iwb200_job *job, const DevInput &in, const DevOutput &out, int r0, int r1, iwb_stream stream) {
+  iwb200_job::gather_plan &g = job->gather;
+  if (!g.inter) {
+    g.inter = (float *)job->scratch(g.pitch * g.chunk_rows * sizeof(float));
+    if (!g.inter) return false;
+  }
+  job->order_after_stream0(stream);
+  const int nch = g.nch;
+  const uint8_t *src0 = in.pix + (ptrdiff_t)(in.y0 - in.row_origin) * (ptrdiff_t)in.bpr + (size_t)in.x0 * nch * (g.depth16 ? 2 : 1);
+  for (int c0 = r0; c0 < r1; c0 += g.chunk_rows) {
+    const int c1 = std::min(r1, c0 + g.chunk_rows);
+    job->last_path = 3; job->last_c0 = c0; job->last_c1 = c1; job->last_sh = 0; job->last_pitch = g.pitch; job->last_inter = g.inter;
+    job->last_gen = 4;
+    GVJob vj{};
+    GVParams &vp = vj.p;
+    vp.src = src0; vp.bpr = in.bpr; vp.ncols = job->in_w * nch; vp.lut_c = g.lut_c; vp.lut_a = g.lut_a; vp.depth16 = g.depth16;
+    // the tensor covers exactly the rows the caller must provide for these output rows (iwb200_job_band_input_rows);
+    // window rows outside it only meet zero weights and arrive as zeros
+    vp.tm_row0 = job->vtab[0].min_src(c0, c1);
+    vp.tm_rows = job->vtab[0].max_src(c0, c1) - vp.tm_row0 + 1;
+    vp.sc = g.sv; vp.inter = g.inter; vp.pitch = (int)g.pitch; vp.row_base = c0; vp.row_lo = c0; vp.row_hi = c1;
+    vp.intclamp = job->cm.intclamp;
+    vj.W = g.WV; vj.nchp = nch;
+    {
+      prof_scope ps(job, 5, stream);
+      if (!iwg_run_v(vj, (cudaStream_t)stream)) return fail(job, "gather path: no vertical kernel variant");
+      g_launches++;
+    }
+    GHJob hj{};
+    GHParams &hp = hj.p;
+    hp.inter = g.inter; hp.pitch = (int)g.pitch; hp.ncols = job->in_w * nch; hp.row_lo = c0; hp.row_hi = c1; hp.sc = g.sh;
+    hp.out_w = out.width; hp.out = out; hp.cm = job->cm;
+    for (int c = 0; c < 4; c++) hp.ch[c] = g.ch[c < nch ? c : 0];
+    hp.ch_g = g.ch_g;
+    hp.nco = g.nco;
+    hp.jump = job->d_jump; hp.any_random = job->any_random;
+    hj.W = g.WH; hj.nch = nch; hj.nco = g.nco;
+    {
+      prof_scope ps(job, 1, stream);
+      if (!iwg_run_h(hj, (cudaStream_t)stream)) return fail(job, "gather path: no horizontal kernel variant");
+      g_launches++;
+    }
+    if (job->negate || job->clear_transparent) {
+      PostParams pp;
+      pp.out = out; pp.row0 = c0; pp.row1 = c1; pp.negate = job->negate; pp.alpha_ch = job->out_alpha_ch;
+      pp.clear_transparent = job->clear_transparent;
+      for (int c = 0; c < 4; c++) pp.maxcode[c] = c < job->ctx->out_nch ? job->ctx->out_ci[c].maxcode : 0;
+      prof_scope ps(job, 4, stream);
+      launch<PostBody>(pp, (size_t)(c1 - c0) * out.width, stream);
+    }
+  }
+  if (cudaGetLastError() != cudaSuccess) return fail(job, "gather path: kernel launch failed");
+  return true;
+}
 #endif  // !IWB_EMU
 
 static void job_free(iwb200_job *job) {
@@ -1387,8 +1559,12 @@ static iwb200_job *job_build(iw_context *ctx, int device) {
   info.taps_v = taps_v; info.taps_h = taps_h;
 #if !defined(IWB_EMU)
   const char *nofuse = iwb_option(ctx, "cuda:fused");
-  if (!(nofuse && !strcmp(nofuse, "0"))) fused_plan_build(job, &job->fused);
-  info.uses_fused_kernel = job->fused.enabled ? (job->fused.v2 ? 2 : 1) : 0;
+  if (!(nofuse && !strcmp(nofuse, "0"))) {
+    fused_plan_build(job, &job->fused);
+    const char *og = iwb_option(ctx, "cuda:gather");
+    if (!job->fused.enabled && !(og && !strcmp(og, "0"))) gather_plan_build(job);
+  }
+  info.uses_fused_kernel = job->fused.enabled ? (job->fused.v2 ? 2 : 1) : (job->gather.enabled ? 4 : 0);
 #endif
   job->flush_tables();
   return job;
@@ -1500,6 +1676,10 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
     if (!fused_run(job, &job->fused, in, out, r0, r1, stream)) return 0;
     return 1;
   }
+  if (job->gather.enabled) {                                      // (TMA: rows must be 16-byte aligned)
+    const uint8_t *s0 = in.pix + (ptrdiff_t)(in.y0 - in.row_origin) * (ptrdiff_t)in.bpr + (size_t)in.x0 * job->gather.nch * (job->gather.depth16 ? 2 : 1);
+    if (in.bpr % 16 == 0 && ((uintptr_t)s0 & 15) == 0) return gather_run(job, in, out, r0, r1, stream) ? 1 : 0;
+  }
 #endif
   if (!ensure_scratch(job)) return 0;
   job->order_after_stream0(stream);
@@ -1588,6 +1768,14 @@ int iwb200_job_read_intermediate(iwb200_job *job, int ch, float *dst, size_t cap
     return dev_d2h(dst, job->inter[ch], (size_t)nrows * w * sizeof(float), 0, job->err) && dev_sync(0, job->err);
   }
 #if !defined(IWB_EMU)
+  if (job->last_path == 3) {                                     // gather path: interleaved by physical channel
+    const int gn = job->gather.nch, gc = job->gather.chan_of_proc[ch];
+    std::vector<float> tmp((size_t)nrows * job->last_pitch);
+    if (!dev_d2h(tmp.data(), job->last_inter, tmp.size() * sizeof(float), 0, job->err) || !dev_sync(0, job->err)) return 0;
+    for (int j = 0; j < nrows; j++)
+      for (int x = 0; x < w; x++) dst[(size_t)j * w + x] = tmp[(size_t)j * job->last_pitch + (size_t)x * gn + gc];
+    return 1;
+  }
   const int nch = job->fused.nch;
   if (job->fused.nco != nch) ch = 0;                             // gray written as RGB: the three channels share one plane
   if (job->last_path == 2) {
@@ -1710,7 +1898,7 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
   size_t d_bpr = in_bpr;
   size_t col_off = 0, row_bytes = in_bpr;      // the part of each host row that travels
 #if !defined(IWB_EMU)
-  if (job->fused.enabled && job->fused.v2 && !iwb_option(job->ctx, "cuda:keep_pitch")) {
+  if (((job->fused.enabled && job->fused.v2) || job->gather.enabled) && !iwb_option(job->ctx, "cuda:keep_pitch")) {
     // a crop in x: only the cropped columns are copied, and they start an aligned device row (otherwise an odd crop
     // origin would rule the TMA kernels out, and the columns outside the crop would cross PCIe for nothing)
     const size_t bpp = (size_t)job->in.nch_phys * (job->in.depth / 8);

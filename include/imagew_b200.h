@@ -304,7 +304,8 @@ struct iwb200_job_info {
   int in_width_phys, in_height_phys; /* physical (stored) rows/columns of the input buffer */
   size_t in_bpr;
   int bandable;             /* 0 when the job must run as one band (error-diffusion dither) */
-  int uses_fused_kernel;    /* 0: generic per-sample kernels; 1 / 2: streaming kernels of the first / second generation */
+  int uses_fused_kernel;    /* 0: generic per-sample kernels; 1 / 2: streaming kernels of the first / second generation;
+                             * 4: gather-form streaming kernels (images with an alpha channel) */
   double taps_v, taps_h;    /* total filter taps (mul+add pairs) per full image, all channels */
 };
 
@@ -341,7 +342,8 @@ int iwb200_job_read_intermediate(iwb200_job *job, int ch, float *dst, size_t cap
  * vertical + horizontal kernel), the number of launches and their summed duration in ms since the last reset. */
 void iwb200_job_set_profiling(iwb200_job *job, int on);
 /* Kernel generation the job's last launch took: 0 generic per-sample kernels, 1 / 2 streaming kernels of the first /
- * second generation (two kernels per chunk), 3 the fused persistent vertical + horizontal kernel; -1 for a null job.
+ * second generation (two kernels per chunk), 3 the fused persistent vertical + horizontal kernel, 4 the gather-form
+ * streaming kernels (alpha); -1 for a null job.
  * Context option "cuda:gen" = 1 | 2 | 3 forces a generation where the job allows it (3: also for small launches). */
 int iwb200_job_last_kernel_generation(const iwb200_job *job);
 /* Diagnostics: every wait inside the fused kernel is bounded (seconds); a warp that gives up records what it waited for
