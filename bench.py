@@ -254,6 +254,209 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+
+class JobInfo(C.Structure):
+    _fields_ = [("out_width", C.c_int), ("out_height", C.c_int), ("out_imgtype", C.c_int),
+                ("out_bit_depth", C.c_int), ("out_sampletype", C.c_int), ("out_channels", C.c_int),
+                ("out_bpr", C.c_size_t), ("in_width_phys", C.c_int), ("in_height_phys", C.c_int),
+                ("in_bpr", C.c_size_t), ("bandable", C.c_int), ("uses_fused_kernel", C.c_int),
+                ("taps_v", C.c_double), ("taps_h", C.c_double)]
+
+
+def bind_job_api(dll):
+    dll.iwb200_kernel_launch_count.restype = C.c_ulonglong
+    dll.iwb200_job_create.restype = C.c_void_p
+    dll.iwb200_job_create.argtypes = [C.c_void_p, C.c_int]
+    dll.iwb200_job_destroy.argtypes = [C.c_void_p]
+    dll.iwb200_job_run_device.restype = C.c_int
+    dll.iwb200_job_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
+                                          C.c_int, C.c_int, C.c_void_p]
+    dll.iwb200_job_band_input_rows.restype = C.c_int
+    dll.iwb200_job_band_input_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    dll.iwb200_job_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    dll.iwb200_job_reset_stats.argtypes = [C.c_void_p]
+    dll.iwb200_job_kernel_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    dll.iwb200_job_last_kernel_generation.argtypes = [C.c_void_p]
+    dll.iwb200_job_last_error.restype = C.c_char_p
+    dll.iwb200_job_last_error.argtypes = [C.c_void_p]
+    dll.iwb200_job_get_info.argtypes = [C.c_void_p, C.POINTER(JobInfo)]
+
+
+def known_answers():
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "known_answers.json")))
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+def measure_config_brief(lib, name, device, steps=5, warmup=3, e2e_steps=2, options=None):
+    """One other BASELINE configuration on one GPU: device-resident ms per image (CUDA events on the launching stream,
+    L2 defeated by buffer rotation or by the image size itself), end to end through iw_process_image on host buffers,
+    the whole-step roofline fraction, and the FNV-1a-64 of the output against the reference's recorded fingerprint."""
+    import torch
+    dll = lib.dll
+    cfg = configs.get(name)
+    rows = configs.synth_rows(lib, cfg)
+    opts = {"cuda:device": device, **(options or {})}
+    ctx = make_ctx(lib, cfg, rows=None, options=opts)
+    job = dll.iwb200_job_create(ctx, device)
+    if not job:
+        raise SystemExit(f"{name}: job creation failed: " + lib.errmsg(ctx))
+    info = JobInfo()
+    dll.iwb200_job_get_info(job, C.byref(info))
+    out_bytes = info.out_bpr * info.out_height
+    per_set = cfg.in_bytes + out_bytes
+    nbuf = 1 if per_set > 300e6 else min(8, max(2, int(np.ceil(300e6 / per_set)) + 1))
+    host = torch.from_numpy(rows.reshape(-1))
+    d_in = [host.to("cuda") for _ in range(nbuf)]
+    d_out = [torch.empty(out_bytes, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
+    stream = torch.cuda.Stream()
+
+    def step(i):
+        ok = dll.iwb200_job_run_device(job, d_in[i % nbuf].data_ptr(), cfg.in_bpr, 0, d_out[i % nbuf].data_ptr(), info.out_bpr,
+                                       0, info.out_height, stream.cuda_stream)
+        if not ok:
+            raise SystemExit(f"{name}: run_device failed: " + dll.iwb200_job_last_error(job).decode())
+
+    with torch.cuda.stream(stream):
+        for i in range(warmup):
+            step(i)
+        stream.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            step(i)
+        e1.record(stream)
+    stream.synchronize()
+    dev_ms = e0.elapsed_time(e1) / steps
+    gen = int(dll.iwb200_job_last_kernel_generation(job))
+    fnv = "%016x" % configs.fnv1a64(lib, d_out[(steps - 1) % nbuf].cpu().numpy())
+    dll.iwb200_job_destroy(job)
+    lib.iw_destroy_context(ctx)
+    del d_in, d_out
+    torch.cuda.empty_cache()
+
+    def e2e_once():
+        c = make_ctx(lib, cfg, rows=rows, options=opts)
+        t0 = time.perf_counter()
+        ok = lib.iw_process_image(c)
+        dt = time.perf_counter() - t0
+        if not ok:
+            raise SystemExit(f"{name}: iw_process_image failed: " + lib.errmsg(c))
+        lib.iw_destroy_context(c)
+        return dt
+
+    e2e_once()
+    e2e_ms = 1000.0 * sum(e2e_once() for _ in range(e2e_steps)) / e2e_steps
+    peak, _ = measured_peak_hbm()
+    want = known_answers().get(name, {}).get("fnv1a64")
+    return {"workload": f"{name}: {cfg.description}", "in": [cfg.in_w, cfg.in_h], "out": [cfg.out_w, cfg.out_h],
+            "device_ms": dev_ms, "device_mpix_s": cfg.out_mpix / (dev_ms / 1000.0), "e2e_ms": e2e_ms,
+            "e2e_mpix_s": cfg.out_mpix / (e2e_ms / 1000.0), "algorithmic_bytes": per_set,
+            "roofline_frac_whole_step": per_set / (dev_ms * 1e-3) / 1e9 / peak, "kernel_generation": gen,
+            "fnv1a64": fnv, "fnv_matches_reference": (fnv == want) if want else None,
+            "l2_defeat": f"{nbuf} rotating buffer set(s), {nbuf * per_set / 1e6:.0f} MB"}
+
+
+def measure_bands(lib, name, rank, local_rank, world, dist, steps=5, warmup=3):
+    """One large image over all ranks' GPUs: (device) every rank resamples its output-row band from its own
+    slab of input rows (+ filter halo), the bands are gathered to rank 0 with NCCL inside the timed step; (end to end)
+    rank 0 alone calls iw_process_image with cuda:devices = every GPU of the job -- the library itself splits the image,
+    copies each band's rows to its device and the results straight back into the caller's buffer."""
+    import torch
+    from imageworsener_b200 import bands as _bands
+    dll = lib.dll
+    cfg = configs.get(name)
+    rows = configs.synth_rows(lib, cfg)               # every rank generates the same image, uploads only its slab
+    ctx = make_ctx(lib, cfg, rows=None, options={"cuda:device": local_rank})
+    job = dll.iwb200_job_create(ctx, local_rank)
+    if not job:
+        raise SystemExit(f"{name}: job creation failed: " + lib.errmsg(ctx))
+    info = JobInfo()
+    dll.iwb200_job_get_info(job, C.byref(info))
+    r0, r1 = _bands.band_rows(info.out_height, rank, world)
+    hmax = max(b - a for a, b in _bands.all_bands(info.out_height, world))
+    first, last = C.c_int(0), C.c_int(0)
+    dll.iwb200_job_band_input_rows(job, r0, r1, C.byref(first), C.byref(last))
+    slab = torch.from_numpy(rows[first.value:last.value + 1].reshape(-1)).to("cuda")
+    d_out = torch.empty(hmax * info.out_bpr, dtype=torch.uint8, device="cuda")
+    gathered = [torch.empty(hmax * info.out_bpr, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+    stream = torch.cuda.Stream()
+
+    def step():
+        ok = dll.iwb200_job_run_device(job, slab.data_ptr(), cfg.in_bpr, first.value, d_out.data_ptr(), info.out_bpr, r0, r1,
+                                       stream.cuda_stream)
+        if not ok:
+            raise SystemExit(f"{name}: run_device failed: " + dll.iwb200_job_last_error(job).decode())
+        dist.gather(d_out, gather_list=gathered, dst=0)
+
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    fnv = None
+    if rank == 0:
+        parts = []
+        for k, (a, b) in enumerate(_bands.all_bands(info.out_height, world)):
+            parts.append(gathered[k][: (b - a) * info.out_bpr].cpu().numpy())
+        fnv = "%016x" % configs.fnv1a64(lib, np.concatenate(parts))
+    dll.iwb200_job_destroy(job)
+    lib.iw_destroy_context(ctx)
+    del slab, d_out, gathered
+    torch.cuda.empty_cache()
+    # (the other ranks wait on the CPU: an NCCL barrier would keep a kernel spinning on the very GPUs rank 0 is about to use)
+    cpu_group = dist.new_group(backend="gloo")
+    dist.barrier(group=cpu_group)
+
+    # end to end: one process, one call, N devices
+    e2e_ms = e2e_1 = None
+    fnv_e2e = None
+    if rank == 0:
+        def once(devs):
+            c = make_ctx(lib, cfg, rows=rows, options={"cuda:devices": ",".join(str(d) for d in devs)})
+            t0 = time.perf_counter()
+            ok = lib.iw_process_image(c)
+            dt = time.perf_counter() - t0
+            if not ok:
+                raise SystemExit(f"{name}: iw_process_image (cuda:devices) failed: " + lib.errmsg(c))
+            img, px = lib.get_output_numpy(c)
+            lib.iw_destroy_context(c)
+            return dt, px
+        devs = list(range(world))
+        once(devs)
+        ts = []
+        for _ in range(3):
+            dt, px = once(devs)
+            ts.append(dt)
+        e2e_ms = 1000.0 * sum(ts) / len(ts)
+        fnv_e2e = "%016x" % configs.fnv1a64(lib, px)
+        once([0])
+        e2e_1 = 1000.0 * once([0])[0]
+    dist.barrier(group=cpu_group)
+    if rank != 0:
+        return None
+    want = known_answers().get(name, {}).get("fnv1a64")
+    return {"workload": f"{name}: {cfg.description}", "in": [cfg.in_w, cfg.in_h], "out": [cfg.out_w, cfg.out_h], "bands": world,
+            "device_ms": dev_ms, "device_mpix_s": cfg.out_mpix / (dev_ms / 1000.0),
+            "device_note": "per step: every rank's band kernels + NCCL gather of the bands to rank 0, max over ranks",
+            "e2e_ms": e2e_ms, "e2e_mpix_s": cfg.out_mpix / (e2e_ms / 1000.0), "e2e_ms_one_device": e2e_1,
+            "e2e_note": "iw_process_image on rank 0 with cuda:devices=0..N-1 (host buffers; bands copied to / from N devices in parallel)",
+            "fnv1a64_device": fnv, "fnv1a64_e2e": fnv_e2e,
+            "fnv_matches_reference": (fnv == want and fnv_e2e == want) if want else None}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -264,6 +467,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="context option name=value (tuning)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the other BASELINE configurations / the band block")
     ap.add_argument("--shard", default="images", choices=["images", "bands"],
                     help="N>1: one image per GPU (weak scaling, default) or one image split into output-row bands "
                          "gathered to rank 0 over NCCL (strong scaling)")
@@ -298,27 +502,8 @@ def main():
 
     lib = L.load_product()
     dll = lib.dll
-    dll.iwb200_kernel_launch_count.restype = C.c_ulonglong
-    dll.iwb200_job_create.restype = C.c_void_p
-    dll.iwb200_job_create.argtypes = [C.c_void_p, C.c_int]
-    dll.iwb200_job_destroy.argtypes = [C.c_void_p]
-    dll.iwb200_job_run_device.restype = C.c_int
-    dll.iwb200_job_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
-                                          C.c_int, C.c_int, C.c_void_p]
-    dll.iwb200_job_set_profiling.argtypes = [C.c_void_p, C.c_int]
-    dll.iwb200_job_reset_stats.argtypes = [C.c_void_p]
-    dll.iwb200_job_kernel_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
-    dll.iwb200_job_last_kernel_generation.argtypes = [C.c_void_p]
-    dll.iwb200_job_last_error.restype = C.c_char_p
-    dll.iwb200_job_last_error.argtypes = [C.c_void_p]
-
-    class Info(C.Structure):
-        _fields_ = [("out_width", C.c_int), ("out_height", C.c_int), ("out_imgtype", C.c_int),
-                    ("out_bit_depth", C.c_int), ("out_sampletype", C.c_int), ("out_channels", C.c_int),
-                    ("out_bpr", C.c_size_t), ("in_width_phys", C.c_int), ("in_height_phys", C.c_int),
-                    ("in_bpr", C.c_size_t), ("bandable", C.c_int), ("uses_fused_kernel", C.c_int),
-                    ("taps_v", C.c_double), ("taps_h", C.c_double)]
-    dll.iwb200_job_get_info.argtypes = [C.c_void_p, C.POINTER(Info)]
+    bind_job_api(dll)
+    Info = JobInfo
 
     cfg = configs.get(args.config)
     rows = configs.synth_rows(lib, cfg, seed=configs.XORSHIFT_SEED + rank)
@@ -466,6 +651,19 @@ def main():
                "sample": f"one full {cfg.in_w}x{cfg.in_h} image through the unmodified reference build, 1 thread "
                          f"(it has no intra-image threading), {dt:.1f} s", "host_cores_available": os.cpu_count()}
 
+    # ---------------- the other BASELINE configurations (N = 1) / one large image in bands over all GPUs (N > 1) ------
+    other, bands_block = None, None
+    if not args.no_other_configs and args.config == "cfg2":
+        if world == 1:
+            other = {}
+            for nm in ("cfg3", "cfg4auto", "cfg4box", "cfg5"):
+                try:
+                    other[nm] = measure_config_brief(lib, nm, local_rank)
+                except SystemExit as e:  # noqa: PERF203
+                    other[nm] = {"error": str(e)}
+        else:
+            bands_block = measure_bands(lib, "cfg5", rank, local_rank, world, dist)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if band_mode else "weak",
@@ -477,6 +675,10 @@ def main():
                            "kernel_generation": kernel_generation, "host_numa_binding": numa},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu}
+        if other is not None:
+            line["other_configs"] = other
+        if bands_block is not None:
+            line["bands"] = bands_block
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -33,7 +33,7 @@
 #define IWG_V_G 8                // vertical: input rows per pipeline stage
 #define IWG_V_NST 4
 #define IWG_H_KP 4               // horizontal: input pixels per pipeline stage
-#define IWG_H_NST 3
+#define IWG_H_NST 4
 #define IWG_WARPS 4
 #define IWG_OST_PITCH 132        // bytes per output staging row (33 words: lane-private banks); <= 128 bytes staged
 

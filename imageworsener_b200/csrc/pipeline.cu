@@ -1603,7 +1603,11 @@ iwb200_job *iwb200_job_create(struct iw_context *ctx, int device) {
     if (!iwb_prepare(ctx)) return nullptr;
   }
   std::string key = plan_key(ctx, device);
-  if (pool_enabled()) {
+  // (context option cuda:plan_cache=0: build this context's job from scratch and do not park it afterwards)
+  const char *pc = iwb_option(ctx, "cuda:plan_cache");
+  const bool use_pool = pool_enabled() && !(pc && pc[0] == '0');
+  if (!use_pool) key.clear();
+  if (use_pool) {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     for (size_t i = g_pool.size(); i-- > 0;)
       if (g_pool[i]->key == key) {

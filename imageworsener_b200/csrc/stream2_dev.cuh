@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, iwb2_v_minb(S))
   // columns outside the tensor are zero-filled and never consumed) + the G schedule rows of weights
   auto fill = [&](int n, int slot) {
     if (s2_elect()) {
+      s2_fence_async();   // this warp's earlier (generic-proxy) reads of the slot are ordered before the bulk copy into it
       const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE;
       s2_mbar_expect(bar, G * TW + G * SS * 8);
       s2_tma_2d(dst, &tmap, wcol0 * (TW / 128), r0 + n * G - p.tm_row0, bar);
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, iwb2_v_minb(S))
   };
   auto fill_u = [&](int n, int slot) {                          // uniform path: stage n = cycle n (+1 of overrun)
     if (s2_elect()) {
+      s2_fence_async();   // this warp's earlier (generic-proxy) reads of the slot are ordered before the bulk copy into it
       const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE_U;
       s2_mbar_expect(bar, GU * TW + GU * SS * 8);
       s2_tma_2d(dst, &tmap_u, wcol0 * (TW / 128), R0 + n * GU - p.tm_row0, bar);
@@ -525,6 +527,7 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
   const int gskip = (b0 * NCH + p.sh) & 3;                      // (KP*NCH is a multiple of 4: the same for every stage)
   auto fill = [&](int n, int slot) {
     if (s2_elect()) {
+      s2_fence_async();   // this warp's earlier (generic-proxy) reads of the slot are ordered before the bulk copy into it
       const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE;
       s2_mbar_expect(bar, 32 * TP * 4 + KP * SS * 8);
       s2_tma_2d(dst, &tmap, (b0 + n * KP) * NCH + p.sh - gskip, grp * 32, bar);
@@ -533,6 +536,7 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
   };
   auto fill_u = [&](int n, int slot) {
     if (s2_elect()) {
+      s2_fence_async();   // this warp's earlier (generic-proxy) reads of the slot are ordered before the bulk copy into it
       const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE_U;
       s2_mbar_expect(bar, 32 * TPU * 4 + GU * SS * 8);
       s2_tma_2d(dst, &tmap_u, (B0 + n * GU) * NCH + p.sh, grp * 32, bar);

@@ -128,6 +128,7 @@ __device__ __forceinline__ void s3_v_item(const V2Params &p, const CUtensorMap *
   }
   auto fill = [&](int n, int slot) {
     if (s2_elect()) {
+      s2_fence_async();   // this warp's earlier (generic-proxy) reads of the slot are ordered before the bulk copy into it
       const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE;
       s2_mbar_expect(bar, G * TW + G * SS * 8);
       s2_tma_2d(dst, tmap, wcol0 * (TW / 128), r0 + n * G - p.tm_row0, bar);
@@ -136,6 +137,7 @@ __device__ __forceinline__ void s3_v_item(const V2Params &p, const CUtensorMap *
   };
   auto fill_u = [&](int n, int slot) {
     if (s2_elect()) {
+      s2_fence_async();   // this warp's earlier (generic-proxy) reads of the slot are ordered before the bulk copy into it
       const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE_U;
       s2_mbar_expect(bar, GU * TW + GU * SS * 8);
       s2_tma_2d(dst, tmap_u, wcol0 * (TW / 128), R0 + n * GU - p.tm_row0, bar);
@@ -387,6 +389,7 @@ __device__ __forceinline__ void s3_h_item(const H2Params &p, const CUtensorMap *
   const int gskip = (b0 * NCH + p.sh) & 3;
   auto fill = [&](int n, int slot) {
     if (s2_elect()) {
+      s2_fence_async();   // this warp's earlier (generic-proxy) reads of the slot are ordered before the bulk copy into it
       const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE;
       s2_mbar_expect(bar, 32 * TP * 4 + KP * SS * 8);
       s2_tma_2d(dst, tmap, (b0 + n * KP) * NCH + p.sh - gskip, grp * 32, bar);
@@ -395,6 +398,7 @@ __device__ __forceinline__ void s3_h_item(const H2Params &p, const CUtensorMap *
   };
   auto fill_u = [&](int n, int slot) {
     if (s2_elect()) {
+      s2_fence_async();   // this warp's earlier (generic-proxy) reads of the slot are ordered before the bulk copy into it
       const unsigned bar = bar0 + 8 * slot, dst = ring0 + slot * STAGE_U;
       s2_mbar_expect(bar, 32 * TPU * 4 + GU * SS * 8);
       s2_tma_2d(dst, tmap_u, (B0 + n * GU) * NCH + p.sh, grp * 32, bar);

@@ -109,3 +109,20 @@ def test_cfg3_quarter_scale(prod, ref):
     _, a = configs.run_host(prod, cfg, rows)
     _, b = configs.run_host(ref, cfg, rows)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("depth", [8, 16])
+def test_fresh_jobs_in_bands_repeatedly(prod, ref, depth):
+    """Regression: a band's pipeline ends with stages that lie outside the band's slab of input rows; the copy engine
+    zero-fills those within a few cycles, which once overtook the last shared-memory reads of the slot being refilled
+    (six wrong output rows in one warp column, a few times in ten runs, only with freshly built jobs).  Every job here
+    is built from scratch (cuda:plan_cache=0)."""
+    cfg = configs.Config("bands", 300, 260, RGBA, depth, 450, 390, "-width 450 -height 390 -filter mitchell -depth 16 -bkgd e42")
+    rows = configs.synth_rows(prod, cfg)
+    _, b = configs.run_host(ref, cfg, rows)
+    for it in range(12):
+        parts = [configs.run_host(prod, cfg, rows, options={"cuda:band": f"{i}/5", "cuda:plan_cache": 0})[1] for i in range(5)]
+        assert np.array_equal(np.concatenate(parts, axis=0), b), f"iteration {it}"
+        _, a = configs.run_host(prod, cfg, rows, options={"cuda:devices": "0,0,0,0,0", "cuda:plan_cache": 0})
+        assert np.array_equal(a, b), f"iteration {it} (threads)"
