@@ -25,6 +25,7 @@
 #include "stream2.cuh"
 #include "stream3.cuh"
 #include "gather4.cuh"
+#include "errdiff.cuh"
 #endif
 
 // ------------------------------------------------------------------------------------------------------
@@ -254,6 +255,7 @@ struct iwb200_job {
   int last_path = -1, last_c0 = 0, last_c1 = 0, last_sh = 0;
   int last_gen = 0;                 // kernel generation of the last launch (0 generic, 1 / 2 streaming, 3 fused)
   int x0_override = -1;             // set by run_host while its device copy holds only the cropped columns
+  DevChanOut *ed_ch_g = nullptr;    // error-diffusion kernel: channel descriptions in global memory
   iwb_timings *tm_sink = nullptr;   // where run_host reports its phase times (default: the context's record)
   int float_prepass = 0;            // float input in a non-linear colourspace: run_host linearises it on the host first
   int prepass_done = 0;             // (set by run_host around its run_device calls)
@@ -1735,6 +1737,38 @@ int iwb200_job_run_device(iwb200_job *job, const void *d_in, size_t in_bpr, int 
           ep.ch[k] = job->cout[p]; ep.lin_plane[k] = job->lin_plane[p]; ep.err[k] = job->errrows[p];
           memcpy(ep.m[k], job->errdiff_m[p], sizeof ep.m[k]);
         }
+#if !defined(IWB_EMU)
+      // one warp per channel with the error rows in shared memory (errdiff.cuh) when a row fits; the per-thread
+      // reference kernel otherwise
+      const size_t ed_smem = iwb_errdiff_smem(W);
+      if (ed_smem <= 220 * 1024 && !iwb_option(job->ctx, "cuda:errdiff_generic")) {
+        if (!job->ed_ch_g) {
+          job->ed_ch_g = (DevChanOut *)job->scratch(4 * sizeof(DevChanOut));
+          if (!job->ed_ch_g) return 0;
+          job->order_after_stream0(stream);
+        }
+        ErrDiffFastParams fp;
+        fp.out = ep.out; fp.nch = ep.nch; fp.row0 = ep.row0; fp.row1 = ep.row1; fp.ch_g = job->ed_ch_g;
+        for (int k = 0; k < ep.nch; k++) {
+          fp.ch[k] = ep.ch[k]; fp.lin_plane[k] = ep.lin_plane[k]; fp.err[k] = ep.err[k];
+          memcpy(fp.m[k], ep.m[k], sizeof fp.m[k]);
+        }
+        cudaMemcpyAsync(job->ed_ch_g, fp.ch, 4 * sizeof(DevChanOut), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+        static std::atomic<unsigned long long> attr{0};
+        once_per_device(attr, [] {
+          cudaFuncSetAttribute(iwb_errdiff_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+          cudaFuncSetAttribute(iwb_errdiff_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        });
+        // Floyd-Steinberg on every channel: the specialised chain (errdiff.cuh)
+        bool fs = true;
+        for (int k = 0; k < ep.nch; k++)
+          for (int i = 0; i < 12; i++) fs = fs && (ep.m[k][i] != 0.0) == (i == 0 || i == 3 || i == 4 || i == 5);
+        prof_scope ps(job, 3, stream);
+        if (fs) iwb_errdiff_warp<true><<<ep.nch, 32, ed_smem, (cudaStream_t)stream>>>(fp);
+        else iwb_errdiff_warp<false><<<ep.nch, 32, ed_smem, (cudaStream_t)stream>>>(fp);
+        g_launches++;
+      } else
+#endif
       { prof_scope ps(job, 3, stream); launch_serial<ErrDiffBody>(ep, ep.nch, stream); }
       job->errdiff_next_row = c1;
     }
