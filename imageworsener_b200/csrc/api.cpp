@@ -177,6 +177,8 @@ void iw_destroy_context(struct iw_context *ctx) {
   if (!ctx) return;
   if (ctx->img1.pixels) iw_free(ctx, ctx->img1.pixels);
   if (ctx->img2.pixels) iw_free(ctx, ctx->img2.pixels);
+  if (ctx->opt_pixels) iw_free(ctx, ctx->opt_pixels);
+  if (ctx->palette) iw_free(ctx, ctx->palette);
   if (ctx->error_msg) iw_free(ctx, ctx->error_msg);
   iw_freefn_type ff = ctx->freefn;
   void *ud = ctx->userdata;
@@ -392,6 +394,8 @@ void iw_get_output_image(struct iw_context *ctx, struct iw_image *img) {
   img->has_bkgdlabel = ctx->res_has_label;
   for (int k = 0; k < 4; k++)
     img->bkgdlabel.c[k] = ((double)ctx->res_label[k]) / (ctx->res_depth == 8 ? 255.0 : 65535.0);
+  img->has_colorkey_trns = ctx->res_has_colorkey;
+  for (int k = 0; k < 3; k++) img->colorkey[k] = ctx->res_colorkey[k];
   if (ctx->reduced_out_maxcode) {
     img->reduced_maxcolors = 1;
     bool alpha = IW_IMGTYPE_HAS_ALPHA(img->imgtype);
@@ -405,7 +409,7 @@ void iw_get_output_image(struct iw_context *ctx, struct iw_image *img) {
   }
 }
 void iw_get_output_colorspace(struct iw_context *ctx, struct iw_csdescr *cs) { *cs = ctx->img2cs; }
-const struct iw_palette *iw_get_output_palette(struct iw_context *) { return nullptr; }  // optimiser: out of scope
+const struct iw_palette *iw_get_output_palette(struct iw_context *ctx) { return ctx->palette; }
 
 // ------------------------------------------------------------------ key/value (src/imagew-api.c:760-994)
 void iw_set_value(struct iw_context *ctx, int code, int n) {

@@ -139,7 +139,16 @@ struct iw_context {
   unsigned int res_label[4] = {0, 0, 0, 0};
   int band_row0 = 0, band_row1 = 0;
   iwb_timings timings;
+  // post-pass optimiser (optimize.h): the optimised image (when it differs from img2), its palette, colour key
+  iw_byte *opt_pixels = nullptr;
+  iw_palette *palette = nullptr;
+  int res_has_colorkey = 0;
+  unsigned int res_colorkey[3] = {0, 0, 0};
 };
+
+struct iwb200_job;
+void iwb_set_result_view(iw_context *ctx, int r0, int r1);                       // process.cpp
+extern "C" int iwb_optimize_output(iw_context *ctx, iwb200_job **jobs, const int *bands, int n);   // pipeline.cu
 
 // ---- page-locked host pool (pipeline.cu) ----
 void *iwb_pinned_alloc(size_t n);   // nullptr when unavailable

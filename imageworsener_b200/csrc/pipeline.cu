@@ -19,6 +19,7 @@
 
 #include "iwb_internal.h"
 #include "kernels.cuh"
+#include "optimize.h"
 #if !defined(IWB_EMU)
 #include <cuda_runtime.h>
 #include "fused.cuh"
@@ -256,6 +257,10 @@ struct iwb200_job {
   int last_gen = 0;                 // kernel generation of the last launch (0 generic, 1 / 2 streaming, 3 fused)
   int x0_override = -1;             // set by run_host while its device copy holds only the cropped columns
   DevChanOut *ed_ch_g = nullptr;    // error-diffusion kernel: channel descriptions in global memory
+  // post-pass optimiser (optimize.h): scan result, rewrite recipe and rewritten band in device memory
+  IwbOptScan *d_scan = nullptr;
+  OptRecipe *d_recipe = nullptr;
+  void *d_opt = nullptr; size_t d_opt_bytes = 0;
   iwb_timings *tm_sink = nullptr;   // where run_host reports its phase times (default: the context's record)
   int float_prepass = 0;            // float input in a non-linear colourspace: run_host linearises it on the host first
   int prepass_done = 0;             // (set by run_host around its run_device calls)
@@ -1256,6 +1261,7 @@ static void job_free(iwb200_job *job) {
   for (void *p : job->allocs) dev_free(p);
   dev_free(job->d_in);
   dev_free(job->d_out);
+  dev_free(job->d_opt);
   delete job;
 }
 
@@ -2051,6 +2057,85 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
 }
 
 
+// ---- post-pass optimiser: device scan -> host decisions -> device rewrite (optimize.h, optimize.cpp) -----------------
+// `jobs[i]` has just produced output rows bands[i] = [r0, r1) of the image in its device output buffer (row pitch
+// ctx->img2.bpr) and copied them to ctx->img2.pixels.  On return the context's result view (iw_get_output_image) is
+// the optimised image; the image as processed stays in ctx->img2.
+int iwb_optimize_output(struct iw_context *ctx, iwb200_job **jobs, const int *bands, int n) {
+  if (ctx->img2.sampletype != IW_SAMPLETYPE_UINT || ctx->reduced_out_maxcode) return 1;   // (src/imagew-opt.c:1196-1204)
+  bool any = false;
+  for (int k = 1; k <= 5; k++) any = any || ctx->opt_flags[k];
+  if (!any) return 1;
+  const int W = ctx->img2.width, H = ctx->img2.height;
+  const int nch = iw_imgtype_num_channels(ctx->img2.imgtype), bps = ctx->img2.bit_depth / 8;
+  const unsigned palbits = IW_PROFILE_PAL1 | IW_PROFILE_PAL2 | IW_PROFILE_PAL4 | IW_PROFILE_PAL8 | IW_PROFILE_GRAY1 | IW_PROFILE_GRAY2 | IW_PROFILE_GRAY4;
+  const int want_colors = (ctx->output_profile & palbits) ? 1 : 0;
+  IwbOptScan merged;
+  memset(&merged, 0, sizeof merged);
+  std::vector<IwbOptScan> part(n);
+  for (int i = 0; i < n; i++) {
+    iwb200_job *job = jobs[i];
+    dev_guard on_device(job->device);
+    iwb_stream st = (iwb_stream)job->streams[1];
+    if (!job->d_scan) {
+      job->d_scan = (IwbOptScan *)job->scratch(sizeof(IwbOptScan));
+      job->d_recipe = (OptRecipe *)job->scratch(sizeof(OptRecipe));
+      if (!job->d_scan || !job->d_recipe) return 0;
+      job->order_after_stream0(st);
+    }
+    dev_zero(job->d_scan, sizeof(IwbOptScan), st);
+    OptScanParams sp;
+    sp.out = job->out; sp.out.pix = (uint8_t *)job->d_out; sp.out.bpr = ctx->img2.bpr; sp.out.row_origin = bands[2 * i];
+    sp.row0 = bands[2 * i]; sp.row1 = bands[2 * i + 1];
+    sp.nch = nch; sp.bps = bps; sp.has_alpha = IW_IMGTYPE_HAS_ALPHA(ctx->img2.imgtype) ? 1 : 0; sp.want_colors = want_colors;
+    sp.res = job->d_scan;
+    launch<OptScanBody>(sp, (size_t)(sp.row1 - sp.row0) * W, st);
+    if (!dev_d2h(&part[i], job->d_scan, sizeof(IwbOptScan), st, job->err)) return 0;
+  }
+  for (int i = 0; i < n; i++) {
+    dev_guard on_device(jobs[i]->device);
+    if (!dev_sync((iwb_stream)jobs[i]->streams[1], jobs[i]->err)) return 0;
+    if (i == 0) { merged = part[0]; if (merged.ncolors > 256) merged.ncolors = 257; }
+    else iwb_opt_merge(&merged, part[i]);
+  }
+  IwbOptOutcome oc;
+  if (!iwb_opt_decide(ctx, merged, &oc)) return 0;
+  ctx->res_has_colorkey = oc.has_colorkey;
+  for (int k = 0; k < 3; k++) ctx->res_colorkey[k] = oc.colorkey[k];
+  if (!oc.changed) return 1;
+  iw_byte *dst = (iw_byte *)iw_malloc_large(ctx, oc.bpr, (size_t)H);
+  if (!dst) return 0;
+  for (int i = 0; i < n; i++) {
+    iwb200_job *job = jobs[i];
+    dev_guard on_device(job->device);
+    iwb_stream st = (iwb_stream)job->streams[1];
+    const int r0 = bands[2 * i], r1 = bands[2 * i + 1];
+    const size_t bytes = (size_t)(r1 - r0) * oc.bpr;
+    if (job->d_opt_bytes < bytes) {
+      dev_free(job->d_opt);
+      job->d_opt = dev_alloc(bytes, job->err);
+      job->d_opt_bytes = job->d_opt ? bytes : 0;
+      if (!job->d_opt) { iw_free(ctx, dst); return 0; }
+      job->s0_dirty = true;
+      job->order_after_stream0(st);
+    }
+    if (!dev_h2d(job->d_recipe, &oc.recipe, sizeof(OptRecipe), st, job->err)) { iw_free(ctx, dst); return 0; }
+    OptRewriteParams rp;
+    rp.out = job->out; rp.out.pix = (uint8_t *)job->d_out; rp.out.bpr = ctx->img2.bpr; rp.out.row_origin = r0;
+    rp.row0 = r0; rp.row1 = r1; rp.dst = (uint8_t *)job->d_opt; rp.dst_bpr = oc.bpr; rp.rc = job->d_recipe;
+    launch<OptRewriteBody>(rp, (size_t)(r1 - r0) * W, st);
+    if (!dev_d2h(dst + (size_t)r0 * oc.bpr, job->d_opt, bytes, st, job->err)) { iw_free(ctx, dst); return 0; }
+  }
+  for (int i = 0; i < n; i++) {
+    dev_guard on_device(jobs[i]->device);
+    if (!dev_sync((iwb_stream)jobs[i]->streams[1], jobs[i]->err)) { iw_free(ctx, dst); return 0; }
+  }
+  if (ctx->opt_pixels) iw_free(ctx, ctx->opt_pixels);
+  ctx->opt_pixels = dst;
+  ctx->res_type = oc.imgtype; ctx->res_depth = oc.bit_depth; ctx->res_bpr = oc.bpr; ctx->res_pixels = dst;
+  return 1;
+}
+
 // One image on several GPUs (context option cuda:devices, process.cpp).  The job is split into output-row bands, one per
 // listed device; each band has its own job (plan tables on its device), its own host thread and stream set, copies only
 // its input rows + filter halo host -> device and writes its output rows device -> host straight into the caller's
@@ -2090,6 +2175,18 @@ int iwb200_run_host_multi(struct iw_context *ctx, const int *devices, int ndev, 
       ctx->timings.h2d_ms = std::max(ctx->timings.h2d_ms, tms[i].h2d_ms);
       ctx->timings.kernel_ms = std::max(ctx->timings.kernel_ms, tms[i].kernel_ms);
       ctx->timings.d2h_ms = std::max(ctx->timings.d2h_ms, tms[i].d2h_ms);
+    }
+  }
+  if (ok) {
+    std::vector<int> bands;
+    for (int i = 0; i < ndev; i++) {
+      bands.push_back((int)(((long long)out_h * i / ndev) / 32 * 32));
+      bands.push_back(i + 1 == ndev ? out_h : (int)(((long long)out_h * (i + 1) / ndev) / 32 * 32));
+    }
+    iwb_set_result_view(ctx, 0, out_h);
+    if (!iwb_optimize_output(ctx, jobs.data(), bands.data(), ndev)) {
+      ok = false;
+      if (!ctx->error_flag) iw_set_error(ctx, "CUDA backend: output optimisation failed");
     }
   }
   for (iwb200_job *j : jobs) if (j) iwb200_job_destroy(j);

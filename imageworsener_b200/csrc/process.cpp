@@ -60,7 +60,6 @@ double now_ms() {
 
 }  // namespace
 
-static int finish_result(struct iw_context *ctx, int r0, int r1);
 extern "C" int iwb200_run_host_multi(struct iw_context *ctx, const int *devices, int ndev, const void *h_in, size_t in_bpr, void *h_out,
                                      size_t out_bpr);
 
@@ -120,7 +119,7 @@ int iw_process_image(struct iw_context *ctx) {
       if (!ctx->error_flag) iw_set_error(ctx, "CUDA backend: multi-device run failed");
       return 0;
     }
-    return finish_result(ctx, 0, ctx->img2.height);
+    return 1;                                                     // (result view and optimiser: inside iwb200_run_host_multi)
   }
   iwb200_job *job = iwb200_job_create(ctx, device);
   if (!job) {
@@ -162,20 +161,27 @@ int iw_process_image(struct iw_context *ctx) {
 
   int ok = iwb200_job_run_host(job, ctx->img1.pixels, ctx->img1.bpr, ctx->img2.pixels, ctx->img2.bpr, r0, r1);
   if (!ok) iw_set_errorf(ctx, "CUDA backend: %s", iwb200_job_last_error(job));
+  if (ok) {
+    iwb_set_result_view(ctx, r0, r1);
+    // the post-pass optimiser (src/imagew-opt.c) while the result is still in HBM; a single band of an image is handed
+    // back as processed (bands of one image must stay concatenable)
+    if (r0 == 0 && r1 == info.out_height) {
+      const int band[2] = {r0, r1};
+      ok = iwb_optimize_output(ctx, &job, band, 1);
+      if (!ok && !ctx->error_flag) iw_set_errorf(ctx, "CUDA backend: output optimisation failed: %s", iwb200_job_last_error(job));
+    }
+  }
   iwb200_job_destroy(job);
-  if (!ok) return 0;
-
-  return finish_result(ctx, r0, r1);
+  return ok ? 1 : 0;
 }
 
 }  // extern "C"
 
-// what follows the kernels: background-colour label and the result view handed out by iw_get_output_image
-static int finish_result(struct iw_context *ctx, int r0, int r1) {
+// what follows the kernels: background-colour label and the result view handed out by iw_get_output_image (the image
+// as processed; the optimiser may replace it, pipeline.cu:iwb_optimize_output).  The optimiser's always-on prologue
+// (transparent pixels -> black, src/imagew-opt.c:1112-1163) ran on the device.
+void iwb_set_result_view(struct iw_context *ctx, int r0, int r1) {
   make_output_label(ctx);
-
-  // The reference's post-pass optimiser (src/imagew-opt.c) is outside this library's scope; the result view
-  // is the image as processed.  Its always-on prologue (transparent pixels -> black) ran on the device.
   ctx->res_w = ctx->img2.width;
   ctx->res_h = r1 - r0;
   ctx->res_type = ctx->img2.imgtype;
@@ -187,7 +193,6 @@ static int finish_result(struct iw_context *ctx, int r0, int r1) {
     for (int k = 0; k < 4; k++)
       ctx->res_label[k] = iw_color_get_int_sample(&ctx->img2.bkgdlabel, k, ctx->img2.bit_depth == 8 ? 255 : 65535);
   }
-  return 1;
 }
 
 extern "C" {
