@@ -453,7 +453,7 @@ int iw_get_value(struct iw_context *ctx, int code) {
     case IW_VAL_INPUT_IMAGE_TYPE: return ctx->img1.imgtype;
     case IW_VAL_INPUT_DEPTH: return ctx->img1.bit_depth;
     case IW_VAL_INCLUDE_SCREEN: return ctx->include_screen;
-    case IW_VAL_OUTPUT_PALETTE_GRAYSCALE: return 0;
+    case IW_VAL_OUTPUT_PALETTE_GRAYSCALE: return ctx->palette_is_gray;
     case IW_VAL_USE_BKGD_LABEL: return ctx->use_label_from_file;
     case IW_VAL_MAX_WIDTH: return ctx->max_width;
     case IW_VAL_MAX_HEIGHT: return ctx->max_height;

@@ -139,9 +139,11 @@ struct iw_context {
   unsigned int res_label[4] = {0, 0, 0, 0};
   int band_row0 = 0, band_row1 = 0;
   iwb_timings timings;
+  struct iw_zlib_module *zlib_module = nullptr;   // carried for the file-format modules (src/imagew.h:720-724)
   // post-pass optimiser (optimize.h): the optimised image (when it differs from img2), its palette, colour key
   iw_byte *opt_pixels = nullptr;
   iw_palette *palette = nullptr;
+  int palette_is_gray = 0;      // the palette is the full gray ramp of its depth (IW_VAL_OUTPUT_PALETTE_GRAYSCALE)
   int res_has_colorkey = 0;
   unsigned int res_colorkey[3] = {0, 0, 0};
 };

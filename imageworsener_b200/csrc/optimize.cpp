@@ -197,6 +197,7 @@ int iwb_opt_decide(iw_context *ctx, const IwbOptScan &scan, IwbOptOutcome *out) 
     for (int i = 0; i < pal_n; i++) { P->entry[i].r = pal[i].r; P->entry[i].g = pal[i].g; P->entry[i].b = pal[i].b; P->entry[i].a = pal[i].a; }
     if (ctx->palette) iw_free(ctx, ctx->palette);
     ctx->palette = P;
+    ctx->palette_is_gray = pal_is_gray ? 1 : 0;
     out->has_palette = 1;
   } else {
     // alpha -> colour-key transparency (:1300-1313 and :410-700)

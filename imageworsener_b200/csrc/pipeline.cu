@@ -1862,6 +1862,7 @@ void iwb200_job_reset_stats(iwb200_job *job) {
 }
 int iwb200_job_kernel_stats(iwb200_job *job, int which, int *launches, double *total_ms) {
   if (!job || which < 0 || which >= 8) return 0;
+  dev_guard on_device(job->device);
 #if !defined(IWB_EMU)
   for (auto &t : job->pending) {
     cudaEvent_t a = (cudaEvent_t)t.a, b = (cudaEvent_t)t.b;
@@ -1893,6 +1894,7 @@ uint64_t iwb200_fnv1a64(const uint8_t *buf, size_t n) {
 int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *h_out, size_t out_bpr, int r0,
                         int r1) {
   if (!job) return 0;
+  dev_guard on_device(job->device);                             // (every allocation below belongs to the job's device)
   int first, last;
   if (!iwb200_job_band_input_rows(job, r0, r1, &first, &last)) return fail(job, "invalid output row band");
   first = std::max(first, 0);
@@ -1970,7 +1972,6 @@ int iwb200_job_run_host(iwb200_job *job, const void *h_in, size_t in_bpr, void *
   // Software pipeline over output-row sub-bands: while sub-band k computes, the input rows of k+1 arrive and the
   // output rows of k-1 leave (three streams, page-locked host buffers).  The kernels take a fraction of the PCIe
   // time, so the call costs about one H2D of the image.  Sequential (error-diffusion) jobs use one sub-band.
-  dev_guard on_device(job->device);
   if (!job->streams[0])
     for (int k = 0; k < 3; k++) { cudaStream_t st; cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking); job->streams[k] = st; }
   cudaStream_t s_in = (cudaStream_t)job->streams[0], s_k = (cudaStream_t)job->streams[1], s_out = (cudaStream_t)job->streams[2];

@@ -36,15 +36,15 @@ typedef CUresult (*iwb2_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_
                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static inline iwb2_encode_fn iwb2_tensor_map_encoder() {        // driver entry point without linking libcuda
-  static iwb2_encode_fn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  // (a function-local static with an initialiser: contexts run concurrently from several host threads, and the first
+  // use must not be seen half done by a second thread)
+  static const iwb2_encode_fn fn = [] {
     void *f = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (iwb2_encode_fn)f;
-  }
+      return (iwb2_encode_fn)f;
+    return (iwb2_encode_fn) nullptr;
+  }();
   return fn;
 }
 

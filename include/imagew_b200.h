@@ -284,6 +284,48 @@ void iw_snprintf(char *buf, size_t buflen, const char *fmt, ...);
 int iw_stricmp(const char *s1, const char *s2);
 void iw_zeromem(void *mem, size_t n);
 
+/* ---- host utilities used by the reference's command-line tool and file-format modules (src/imagew.h:667-810;
+ * csrc/util.cpp).  They let the UNMODIFIED imagew-cmd.c and imagew-{pnm,bmp,miff,tiff,gif,allfmts}.c link against this
+ * library. ---- */
+#include <stdarg.h>
+#define IW_ENDIAN_BIG 0
+#define IW_ENDIAN_LITTLE 1
+#define IW_TRANSLATEFLAG_FORMAT 0x0001
+#define IW_TRANSLATEFLAG_POSTFORMAT 0x0002
+#define IW_TRANSLATEFLAG_ERRORMSG 0x0010
+#define IW_TRANSLATEFLAG_WARNINGMSG 0x0020
+struct iw_zlib_module;
+void iw_vsnprintf(char *buf, size_t buflen, const char *fmt, va_list ap);
+void iw_translate(struct iw_context *ctx, unsigned int flags, char *dst, size_t dstlen, const char *src);
+void iw_translatev(struct iw_context *ctx, unsigned int flags, char *dst, size_t dstlen, const char *fmt, va_list ap);
+void iw_translatef(struct iw_context *ctx, unsigned int flags, char *dst, size_t dstlen, const char *fmt, ...);
+char *iw_get_copyright_string(struct iw_context *ctx, char *dst, int dstlen);
+void iw_utf8_to_ascii(const char *src, char *dst, int dstlen);
+int iw_get_host_endianness(void);
+void iw_set_ui16le(iw_byte *b, unsigned int n);
+void iw_set_ui32le(iw_byte *b, unsigned int n);
+void iw_set_ui16be(iw_byte *b, unsigned int n);
+void iw_set_ui32be(iw_byte *b, unsigned int n);
+unsigned int iw_get_ui16le(const iw_byte *b);
+unsigned int iw_get_ui32le(const iw_byte *b);
+int iw_get_i32le(const iw_byte *b);
+unsigned int iw_get_ui16be(const iw_byte *b);
+unsigned int iw_get_ui32be(const iw_byte *b);
+unsigned int iw_get_ui16_e(const iw_byte *b, int endian);
+unsigned int iw_get_ui32_e(const iw_byte *b, int endian);
+int iw_max_color_to_bitdepth(unsigned int mc);
+int iw_detect_fmt_from_filename(const char *fn);
+const char *iw_get_fmt_name(int fmt);
+int iw_detect_fmt_of_file(const iw_byte *buf, size_t n);
+int iw_is_input_fmt_supported(int fmt);
+int iw_is_output_fmt_supported(int fmt);
+int iw_parse_number_list(const char *s, int max_numbers, double *results);
+double iw_parse_number(const char *s);
+int iw_round_to_int(double x);
+int iw_parse_int(const char *s);
+void iw_set_zlib_module(struct iw_context *ctx, struct iw_zlib_module *z);
+struct iw_zlib_module *iw_get_zlib_module(struct iw_context *ctx);
+
 /* =========================================== B200 extensions ============================================ */
 
 /* Library identification: "imagew_b200 <version> sm_100a" (or "... host-emulation" for the test-only build). */

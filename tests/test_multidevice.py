@@ -63,7 +63,7 @@ def test_error_diffusion_refuses_cuda_devices(prod):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("bad", ["", "a,b", "0,-1", "0;1"])
+@pytest.mark.parametrize("bad", ["a,b", "0,-1", "0;1", ",", "0,1x"])
 def test_malformed_device_lists_fail_loudly(prod, bad):
     cfg = configs.Config("bad", 64, 64, RGB, 8, 32, 32, "-width 32 -height 32")
     rows = configs.synth_rows(prod, cfg)
