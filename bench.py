@@ -457,6 +457,70 @@ def measure_bands(lib, name, rank, local_rank, world, dist, steps=5, warmup=3):
             "fnv_matches_reference": (fnv == want and fnv_e2e == want) if want else None}
 
 
+def measure_batch(lib, name, rank, local_rank, world, dist, total=1024, distinct=64, depth=4):
+    """BASELINE configuration 4: `total` same-shaped images (`distinct` different noise images, cycled) through the batch
+    entry point (iwb200_batch_*), one image per GPU round-robin over the ranks: page-locked host buffers, the copies and
+    kernels of consecutive images overlapped inside the library.  Every distinct image's result is compared with the
+    fingerprint of the first one's known answer where recorded, and all copies of an image must agree."""
+    import torch
+    dll = lib.dll
+    dll.iwb200_batch_create.restype = C.c_void_p
+    dll.iwb200_batch_create.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int]
+    dll.iwb200_batch_submit.restype = C.c_int
+    dll.iwb200_batch_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    dll.iwb200_batch_wait.restype = C.c_int
+    dll.iwb200_batch_wait.argtypes = [C.c_void_p]
+    dll.iwb200_batch_destroy.argtypes = [C.c_void_p]
+    dll.iwb200_batch_last_error.restype = C.c_char_p
+    dll.iwb200_batch_last_error.argtypes = [C.c_void_p]
+    cfg = configs.get(name)
+    mine = total // world
+    nd = min(distinct, mine)
+    ins = torch.empty((nd, cfg.in_bytes), dtype=torch.uint8).pin_memory()
+    for k in range(nd):
+        ins[k].copy_(torch.from_numpy(configs.synth_rows(lib, cfg, seed=configs.XORSHIFT_SEED + 1000 * rank + k).reshape(-1)))
+    ctx = make_ctx(lib, cfg, rows=None, options={"cuda:device": local_rank})
+    devs = (C.c_int * 1)(local_rank)
+    b = dll.iwb200_batch_create(ctx, devs, 1, depth)
+    if not b:
+        raise SystemExit(f"{name}: batch creation failed: " + lib.errmsg(ctx))
+    out_bytes = cfg.out_w * cfg.out_h * cfg.nch
+    outs = torch.zeros((mine, out_bytes), dtype=torch.uint8).pin_memory()
+
+    def run(n):
+        for i in range(n):
+            if not dll.iwb200_batch_submit(b, ins[i % nd].data_ptr(), cfg.in_bpr, outs[i].data_ptr(), cfg.out_w * cfg.nch):
+                raise SystemExit(f"{name}: batch submit failed: " + dll.iwb200_batch_last_error(b).decode())
+        if not dll.iwb200_batch_wait(b):
+            raise SystemExit(f"{name}: batch wait failed: " + dll.iwb200_batch_last_error(b).decode())
+
+    run(min(mine, 64))                                   # warm (plan, pools, clocks)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run(mine)
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    # every copy of a distinct image gives the same bytes; the first image's fingerprint is the recorded known answer
+    o = outs.numpy()
+    consistent = all(np.array_equal(o[i], o[i % nd]) for i in range(mine))
+    fnv0 = "%016x" % configs.fnv1a64(lib, o[0])
+    want = known_answers().get(name, {}).get("fnv1a64") if rank == 0 else None
+    dll.iwb200_batch_destroy(b)
+    lib.iw_destroy_context(ctx)
+    per_img = cfg.in_bytes + out_bytes
+    return {"workload": f"{name}: {cfg.description}", "images": mine * world, "distinct_images_per_gpu": nd, "slots_per_gpu": depth,
+            "seconds": dt, "images_per_s": mine * world / dt, "mpix_s": mine * world * cfg.out_mpix / dt,
+            "pcie_bytes_per_image": per_img, "host_gb_s": mine * world * per_img / dt / 1e9,
+            "copies_of_an_image_agree": bool(consistent),
+            "first_image_fnv_matches_reference": (fnv0 == want) if want else None,
+            "api": "iwb200_batch_submit (page-locked host buffers; H2D + kernels + D2H of consecutive images overlapped)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -652,7 +716,7 @@ def main():
                          f"(it has no intra-image threading), {dt:.1f} s", "host_cores_available": os.cpu_count()}
 
     # ---------------- the other BASELINE configurations (N = 1) / one large image in bands over all GPUs (N > 1) ------
-    other, bands_block = None, None
+    other, bands_block, batch_block = None, None, None
     if not args.no_other_configs and args.config == "cfg2":
         if world == 1:
             other = {}
@@ -663,6 +727,7 @@ def main():
                     other[nm] = {"error": str(e)}
         else:
             bands_block = measure_bands(lib, "cfg5", rank, local_rank, world, dist)
+        batch_block = {nm: measure_batch(lib, nm, rank, local_rank, world, dist if world > 1 else None) for nm in ("cfg4auto", "cfg4box")}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
@@ -679,6 +744,8 @@ def main():
             line["other_configs"] = other
         if bands_block is not None:
             line["bands"] = bands_block
+        if batch_block is not None:
+            line["batch"] = batch_block
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -2194,4 +2194,127 @@ int iwb200_run_host_multi(struct iw_context *ctx, const int *devices, int ndev, 
   return ok ? 1 : 0;
 }
 
+
+struct iwb200_batch;
+void iwb200_batch_destroy(iwb200_batch *b);
+
+// ---- batches of same-shaped images (BASELINE configuration 4: 1024 thumbnails) ------------------------------------------
+// One plan for the whole batch (the context describes the job: input header, size, filter, dither ...; its pixels are
+// not used).  Every listed device gets `depth` slots, each with its own job (tables on that device), staging buffers and
+// stream.  iwb200_batch_submit() queues, on the next slot in round-robin order, the host -> device copy of one image, its
+// kernels and the device -> host copy of its result -- all asynchronous, so image k+1 crosses PCIe while image k
+// computes and image k-1 leaves; the call only blocks when the slot it wants is still busy with an earlier image.
+// Host buffers should be page-locked (iw_malloc_large memory is); pageable memory works but serialises the copies.
+struct iwb200_batch {
+  struct slot { iwb200_job *job = nullptr; void *d_in = nullptr, *d_out = nullptr; void *stream = nullptr, *done = nullptr; bool busy = false; };
+  iw_context *ctx = nullptr;
+  std::vector<slot> slots;
+  size_t next = 0;
+  size_t in_bytes = 0, out_bytes = 0, d_bpr = 0, in_row_bytes = 0;
+  int in_rows = 0, out_rows = 0;
+  std::string err;
+};
+
+static bool batch_finish_slot(iwb200_batch *b, iwb200_batch::slot &s) {
+  if (!s.busy) return true;
+  s.busy = false;
+#if !defined(IWB_EMU)
+  dev_guard on_device(s.job->device);
+  if (const char *m = dev_check(cudaEventSynchronize((cudaEvent_t)s.done))) { b->err = std::string("batch: ") + m; return false; }
+#endif
+  return true;
+}
+
+iwb200_batch *iwb200_batch_create(struct iw_context *ctx, const int *devices, int ndev, int depth) {
+  if (!ctx || ndev < 1 || !devices) return nullptr;
+  depth = std::max(1, std::min(depth, 16));
+  iwb200_batch *b = new iwb200_batch();
+  b->ctx = ctx;
+  for (int d = 0; d < ndev; d++)
+    for (int k = 0; k < depth; k++) {
+      iwb200_batch::slot s;
+      s.job = iwb200_job_create(ctx, devices[d]);
+      if (!s.job) { b->err = "batch: could not build the plan"; b->slots.push_back(s); iwb200_batch_destroy(b); return nullptr; }
+      if (s.job->any_errdiff || s.job->float_prepass) {
+        iw_set_error(ctx, "CUDA backend: batches do not take error-diffusion dithering or non-linear floating-point input");
+        b->slots.push_back(s); iwb200_batch_destroy(b); return nullptr;
+      }
+      dev_guard on_device(s.job->device);
+      const iwb200_job_info &info = s.job->info;
+      b->in_rows = info.in_height_phys; b->out_rows = info.out_height;
+      b->in_row_bytes = info.in_bpr;
+      b->d_bpr = (info.in_bpr + 15) & ~(size_t)15;              // (rows start on 16 bytes on the device: the TMA kernels)
+      b->in_bytes = b->d_bpr * (size_t)info.in_height_phys;
+      b->out_bytes = info.out_bpr * (size_t)info.out_height;
+      s.d_in = dev_alloc(b->in_bytes, b->err);
+      s.d_out = dev_alloc(b->out_bytes, b->err);
+#if !defined(IWB_EMU)
+      cudaStream_t st; cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking); s.stream = st;
+      cudaEvent_t ev; cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); s.done = ev;
+      cudaEventRecord(ev, 0);
+      cudaStreamWaitEvent(st, ev, 0);                           // (the buffers were allocated on the default stream)
+#endif
+      b->slots.push_back(s);
+      if (!s.d_in || !s.d_out) { iwb200_batch_destroy(b); return nullptr; }
+    }
+  return b;
+}
+
+int iwb200_batch_submit(iwb200_batch *b, const void *h_in, size_t in_bpr, void *h_out, size_t out_bpr) {
+  if (!b || !h_in || !h_out) return 0;
+  iwb200_batch::slot &s = b->slots[b->next];
+  b->next = (b->next + 1) % b->slots.size();
+  if (!batch_finish_slot(b, s)) return 0;
+  iwb200_job *job = s.job;
+  dev_guard on_device(job->device);
+  const iwb200_job_info &info = job->info;
+  if (out_bpr != info.out_bpr || in_bpr < b->in_row_bytes) { b->err = "batch: row strides do not match the plan"; return 0; }
+#if defined(IWB_EMU)
+  for (int r = 0; r < b->in_rows; r++) memcpy((uint8_t *)s.d_in + (size_t)r * b->d_bpr, (const uint8_t *)h_in + (size_t)r * in_bpr, b->in_row_bytes);
+  if (!iwb200_job_run_device(job, s.d_in, b->d_bpr, 0, s.d_out, out_bpr, 0, b->out_rows, nullptr)) { b->err = job->err; return 0; }
+  memcpy(h_out, s.d_out, b->out_bytes);
+#else
+  cudaStream_t st = (cudaStream_t)s.stream;
+  cudaError_t e;
+  if (in_bpr == b->d_bpr) e = cudaMemcpyAsync(s.d_in, h_in, b->in_bytes, cudaMemcpyHostToDevice, st);
+  else e = cudaMemcpy2DAsync(s.d_in, b->d_bpr, h_in, in_bpr, b->in_row_bytes, (size_t)b->in_rows, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) { b->err = std::string("batch: H2D copy: ") + cudaGetErrorString(e); return 0; }
+  if (!iwb200_job_run_device(job, s.d_in, b->d_bpr, 0, s.d_out, out_bpr, 0, b->out_rows, st)) { b->err = job->err; return 0; }
+  e = cudaMemcpyAsync(h_out, s.d_out, b->out_bytes, cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) { b->err = std::string("batch: D2H copy: ") + cudaGetErrorString(e); return 0; }
+  cudaEventRecord((cudaEvent_t)s.done, st);
+#endif
+  s.busy = true;
+  return 1;
+}
+
+int iwb200_batch_wait(iwb200_batch *b) {
+  if (!b) return 0;
+  bool ok = true;
+  for (auto &s : b->slots) ok = batch_finish_slot(b, s) && ok;
+  return ok ? 1 : 0;
+}
+
+const char *iwb200_batch_last_error(const iwb200_batch *b) { return b ? b->err.c_str() : "null batch"; }
+int iwb200_batch_get_info(const iwb200_batch *b, struct iwb200_job_info *info) {
+  return (b && !b->slots.empty() && b->slots[0].job) ? iwb200_job_get_info(b->slots[0].job, info) : 0;
+}
+
+void iwb200_batch_destroy(iwb200_batch *b) {
+  if (!b) return;
+  for (auto &s : b->slots) {
+    if (!s.job) continue;
+    dev_guard on_device(s.job->device);
+#if !defined(IWB_EMU)
+    if (s.stream) { cudaStreamSynchronize((cudaStream_t)s.stream); cudaStreamDestroy((cudaStream_t)s.stream); }
+    if (s.done) cudaEventDestroy((cudaEvent_t)s.done);
+    s.job->used_external_stream = 0;                            // (synchronised just above)
+#endif
+    dev_free(s.d_in);
+    dev_free(s.d_out);
+    iwb200_job_destroy(s.job);
+  }
+  delete b;
+}
+
 }  // extern "C"

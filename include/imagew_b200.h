@@ -388,6 +388,23 @@ void iwb200_job_set_profiling(iwb200_job *job, int on);
  * streaming kernels (alpha); -1 for a null job.
  * Context option "cuda:gen" = 1 | 2 | 3 forces a generation where the job allows it (3: also for small launches). */
 int iwb200_job_last_kernel_generation(const iwb200_job *job);
+/* ---- batches of same-shaped images --------------------------------------------------------------------------------
+ * One plan for many images of the same shape and settings (thumbnailing a directory, BASELINE configuration 4).  `ctx`
+ * carries the settings and the input image HEADER (iw_set_input_image with pixels == NULL is enough); it must outlive
+ * the batch.  Every listed device gets `depth` slots; iwb200_batch_submit() queues one image (host -> device copy,
+ * kernels, device -> host copy of the result) on the next slot and returns at once unless that slot is still busy, so
+ * copies and kernels of consecutive images overlap.  `h_out` receives the image as processed (info.out_bpr bytes per
+ * row, iwb200_job_get_info); it is complete after iwb200_batch_wait() or after `depth * ndev` later submissions.
+ * Page-locked host buffers (iw_malloc_large) keep the copies asynchronous.  A batch is used from one thread at a time;
+ * several batches (e.g. one per device) may run from several threads. */
+typedef struct iwb200_batch iwb200_batch;
+iwb200_batch *iwb200_batch_create(struct iw_context *ctx, const int *devices, int ndev, int depth);
+int iwb200_batch_submit(iwb200_batch *b, const void *h_in, size_t in_bpr, void *h_out, size_t out_bpr);
+int iwb200_batch_wait(iwb200_batch *b);
+const char *iwb200_batch_last_error(const iwb200_batch *b);
+int iwb200_batch_get_info(const iwb200_batch *b, struct iwb200_job_info *info);   /* output size, type, depth, row stride */
+void iwb200_batch_destroy(iwb200_batch *b);
+
 /* Diagnostics: every wait inside the fused kernel is bounded (seconds); a warp that gives up records what it waited for
  * and the launch ends with an error instead of hanging the device.  Copies the record as text into buf (empty string
  * if there is none), clears it, returns its length. */
