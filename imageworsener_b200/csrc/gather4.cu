@@ -48,7 +48,7 @@ bool run_v(const GVJob &job, cudaStream_t st) {
   return true;
 }
 
-template <int W, int NCH, int NCO, bool FAST>
+template <int W, int NCH, int NCO, int FAST>
 bool run_h(const GHJob &job, cudaStream_t st) {
   GHParams p = job.p;
   const int threads = 32 * IWG_WARPS;
@@ -60,7 +60,8 @@ bool run_h(const GHJob &job, cudaStream_t st) {
   p.seg = seg;
   constexpr int TP = iwb2_tile_pitch(IWG_H_KP * NCH + 3);
   const size_t stage = ((size_t)32 * TP * 4 + 127) & ~(size_t)127;
-  const size_t smem = (size_t)IWG_WARPS * (IWG_H_NST * stage + 32 * IWG_OST_PITCH + 128) + (size_t)seg * 4 + 16;
+  const size_t smem = (size_t)IWG_WARPS * (IWG_H_NST * stage + 32 * IWG_OST_PITCH + 128) + (FAST == 2 ? IWB_EST_NREC * sizeof(IwbEstRec) : 0) +
+                      (size_t)seg * 4 + 16;
   CUtensorMap tm;
   if (!g4_inter_map(p, TP, &tm)) return false;
   auto kernel = iwg_h<W, NCH, NCO, FAST>;
@@ -91,13 +92,14 @@ bool fast_epilogue(const GHJob &job) {
 template <int W>
 bool run_h_w(const GHJob &job, cudaStream_t st) {
   const bool fast = fast_epilogue(job);
+  const bool model = fast && job.p.est && job.p.ch[0].dfamily == 0 && job.p.ch[0].late_bkgd && job.p.out.depth == 16;
   if (job.nch == 4) {
-    if (job.nco == 4) return run_h<W, 4, 4, false>(job, st);
-    if (job.nco == 3) return fast ? run_h<W, 4, 3, true>(job, st) : run_h<W, 4, 3, false>(job, st);
+    if (job.nco == 4) return run_h<W, 4, 4, 0>(job, st);
+    if (job.nco == 3) return model ? run_h<W, 4, 3, 2>(job, st) : (fast ? run_h<W, 4, 3, 1>(job, st) : run_h<W, 4, 3, 0>(job, st));
     return false;
   }
-  if (job.nco == 2) return run_h<W, 2, 2, false>(job, st);
-  if (job.nco == 1) return fast ? run_h<W, 2, 1, true>(job, st) : run_h<W, 2, 1, false>(job, st);
+  if (job.nco == 2) return run_h<W, 2, 2, 0>(job, st);
+  if (job.nco == 1) return model ? run_h<W, 2, 1, 2>(job, st) : (fast ? run_h<W, 2, 1, 1>(job, st) : run_h<W, 2, 1, 0>(job, st));
   return false;
 }
 

@@ -24,6 +24,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "estimate.h"
 #include "kernels.cuh"
 #include "prng.cuh"
 
@@ -71,6 +72,8 @@ struct GHParams {
   int nco;                       // output channels: output channel k is interleaved channel k (alpha last, kept or dropped)
   const iwb_affine_t *jump;
   int any_random;
+  const IwbEstRec *est;          // level model (estimate.h) of the output channels' common table, or NULL
+  double est_margin;
 };
 
 struct GVJob { GVParams p; int W, nchp; };

@@ -295,6 +295,8 @@ struct iwb200_job {
     float *inter = nullptr;
     int chunk_rows = 0;
     size_t pitch = 0;
+    const IwbEstRec *est = nullptr;               // level model of the colour channels' table (estimate.h), 16-bit output
+    double est_margin = 0.0;
   } gather;
   std::vector<std::unique_ptr<VH3State>> vh3;    // fused-kernel state per row range (stream3.cuh)
   int gen3 = 0;                                 // the fused kernel is opt-in (cuda:gen=3): 0 never, 2 whenever supported
@@ -1173,6 +1175,21 @@ static void gather_plan_build(iwb200_job *job) {
     g.ch_g = job->upload(four, 4);
     if (!g.ch_g) return;
   }
+  g.est = nullptr;
+  {
+    // 16-bit output without dither: a validated model of the table's midpoints (estimate.h) settles almost every sample
+    const DevChanOut &o = g.ch[0];
+    int p0 = -1;
+    for (int p = 0; p < job->nproc; p++) if (g.chan_of_proc[p] == 0) p0 = p;
+    if (p0 >= 0 && ctx->img2.bit_depth == 16 && o.qmode == 1 && !o.codeval && !o.use_nc && o.dfamily == 0 && o.guess_cs >= 0 &&
+        (int)job->thr_host[p0].size() == o.ntab) {
+      IwbEstTable t;
+      if (iwb_build_est_table(o.guess_cs, job->thr_host[p0], &t)) {
+        g.est = job->upload(t.rec.data(), t.rec.size());
+        g.est_margin = t.margin;
+      }
+    }
+  }
   g.vfirst = hv.first; g.vlast = hv.last;
   g.lut_c = lut_c; g.lut_a = lut_a;
   g.nch = nch;
@@ -1222,6 +1239,7 @@ static bool gather_run(iwb200_job *job, const DevInput &in, const DevOutput &out
     hp.ch_g = g.ch_g;
     hp.nco = g.nco;
     hp.jump = job->d_jump; hp.any_random = job->any_random;
+    hp.est = g.est; hp.est_margin = g.est_margin;
     hj.W = g.WH; hj.nch = nch; hj.nco = g.nco;
     {
       prof_scope ps(job, 1, stream);
