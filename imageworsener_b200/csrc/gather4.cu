@@ -1,4 +1,6 @@
 // gather4.cu -- gather-form streaming kernels: instantiations, tensor maps, launch (design: gather4.cuh).
+#include <cmath>
+
 #include "gather4_dev.cuh"
 #include "stream2_host.cuh"
 
@@ -51,20 +53,31 @@ bool run_v(const GVJob &job, cudaStream_t st) {
 template <int W, int NCH, int NCO, int FAST>
 bool run_h(const GHJob &job, cudaStream_t st) {
   GHParams p = job.p;
-  const int threads = 32 * IWG_WARPS;
+  constexpr int NW = iwg_h_warps(FAST), NST = iwg_h_nst(FAST);
+  const int threads = 32 * NW;
   const int groups = (p.row_hi - p.row_lo + 31) / 32;
-  const int rowblocks = (groups + IWG_WARPS - 1) / IWG_WARPS;
-  const int want = std::max(1, (8 * iwb2_sm_count()) / rowblocks);
-  int seg = std::max(64, (p.out_w + want - 1) / want);
-  seg = std::min((seg + 3) & ~3, 4096);
-  p.seg = seg;
+  const int rowblocks = (groups + NW - 1) / NW;
   constexpr int TP = iwb2_tile_pitch(IWG_H_KP * NCH + 3);
   const size_t stage = ((size_t)32 * TP * 4 + 127) & ~(size_t)127;
-  const size_t smem = (size_t)IWG_WARPS * (IWG_H_NST * stage + 32 * IWG_OST_PITCH + 128) + (FAST == 2 ? IWB_EST_NREC * sizeof(IwbEstRec) : 0) +
-                      (size_t)seg * 4 + 16;
+  const size_t smem_fixed = (size_t)NW * (NST * stage + 32 * IWG_OST_PITCH + 128) + (FAST == 2 ? IWB_EST_NREC * sizeof(IwbEstRec) : 0) + 16;
+  auto kernel = iwg_h<W, NCH, NCO, FAST>;
+  // column segments: about 2-3 waves of CTAs, and among the candidates the count whose last wave is fullest
+  const int slots = iwb2_ctas_per_sm(kernel, threads, smem_fixed + 4 * 512) * iwb2_sm_count();
+  const int want = std::max(1, (5 * slots / 2) / rowblocks);
+  int best = 1;
+  double best_eff = 0.0;
+  for (int n = std::max(1, want / 2); n <= want + want / 2 + 1; n++) {
+    if ((p.out_w + n - 1) / n < 64 && n > 1) break;
+    const double waves = (double)n * rowblocks / slots;
+    const double eff = waves / std::ceil(waves) - 0.01 * std::abs(n - want) / want;
+    if (eff > best_eff) { best_eff = eff; best = n; }
+  }
+  int seg = std::max(64, (p.out_w + best - 1) / best);
+  seg = std::min((seg + 3) & ~3, 4096);
+  p.seg = seg;
+  const size_t smem = smem_fixed + (size_t)seg * 4;
   CUtensorMap tm;
   if (!g4_inter_map(p, TP, &tm)) return false;
-  auto kernel = iwg_h<W, NCH, NCO, FAST>;
   iwb2_ctas_per_sm(kernel, threads, smem);
   kernel<<<dim3((unsigned)((p.out_w + seg - 1) / seg), (unsigned)rowblocks), threads, smem, st>>>(tm, p);
   return true;
