@@ -98,3 +98,30 @@ bool iwb_build_est_table(int cstype, const std::vector<double> &thr, IwbEstTable
   // the model must be worth having: most segments valid
   return out->invalid * 8 < nseg;
 }
+
+// test hook (include/imagew_b200.h)
+extern "C" int iwb200_debug_level_model(int cstype, const double *thr, int ntab, const double *v, int n, int *code, double *stats) {
+  IwbEstTable t;
+  if (!iwb_build_est_table(cstype, std::vector<double>(thr, thr + ntab), &t)) return 0;
+  if (stats) { stats[0] = t.margin; stats[1] = t.worst; stats[2] = (double)t.invalid; }
+  const int top = ntab - 1;
+  for (int i = 0; i < n; i++) {
+    // the kernel's steps (gather4_dev.cuh: emit_est), on the host
+    double x = v[i];
+    int h = hi_of(x);
+    uint64_t b;
+    memcpy(&b, &x, 8);
+    b = ((uint64_t)(uint32_t)(h & ~(h >> 31)) << 32) | (b & 0xffffffffu);
+    memcpy(&x, &b, 8);
+    const int hc = iwb_est_clamped_hi(hi_of(x));
+    const double g = iwb_est_eval_rec(t.rec[iwb_est_index(hc)], x, hc);
+    const double tt = g + IWB_EST_MAGIC;
+    const double d = g - (tt - IWB_EST_MAGIC);
+    uint64_t tb;
+    memcpy(&tb, &tt, 8);
+    const int cd = (int)(uint32_t)tb + (hi_of(d) >> 31);
+    const bool slow = !(std::fabs(d) > t.margin) || (unsigned)cd > (unsigned)top;
+    code[i] = slow ? -1 : cd;
+  }
+  return 1;
+}

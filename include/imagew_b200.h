@@ -424,6 +424,12 @@ int iwb200_debug_plan_parts(const int *first, const int *last, int n_out, int lo
 int iwb200_debug_build_schedule(const int *tap_first, const int *tap_src, const double *tap_w, int n_in, int n_out,
                                 int *slots, int *first, int *last, double *w);
 
+/* Test hook: the level model of the 16-bit epilogue (csrc/estimate.h); pure host code, the same arithmetic as the kernel.
+ * Builds the model for a colour space (IW_CSTYPE_*) and a table thr[ntab] (linear value of every code), stores the
+ * measured margin / worst error / number of unvalidated segments in stats[3] and, for each of the n samples v[i], the
+ * code the model settles on or -1 when the sample is left to the table.  Returns 0 if no model exists. */
+int iwb200_debug_level_model(int cstype, const double *thr, int ntab, const double *v, int n, int *code, double *stats);
+
 /* Deterministic synthetic input and output fingerprint used by the benchmarks and the full-size parity tests
  * (SURVEY.md section 8c): xorshift64 noise (s^=s<<13; s^=s>>7; s^=s<<17; byte = s>>24), FNV-1a 64-bit. */
 void iwb200_synth_xorshift(uint8_t *buf, size_t n, uint64_t seed);

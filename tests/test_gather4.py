@@ -35,6 +35,12 @@ SHAPES = [
     ("rgba8_samesize_bkgd", 300, 200, RGBA, 8, 300, 200, "-filter mitchell -bkgd 0a0"),
     ("rgba8_gaussian_w8", 300, 200, RGBA, 8, 420, 280, "-filter gaussian"),
     ("rgba8_negate", 200, 100, RGBA, 8, 300, 150, "-filter catrom -negate"),
+    # 16-bit output without dither: the level model (csrc/estimate.h) settles most samples, the table the rest
+    ("rgba16_model_rec709", 240, 200, RGBA, 16, 700, 555, "-filter catrom -depth 16 -bkgd 2a7 -cs rec709"),
+    ("rgba8_model_to16", 300, 220, RGBA, 8, 640, 480, "-filter lanczos -depth 16 -bkgd fff"),
+    ("rgba16_model_depth12", 256, 256, RGBA, 16, 600, 600, "-filter mitchell -depth 12 -bkgd 000"),
+    ("ga16_model_down", 640, 480, GA, 16, 500, 377, "-filter mitchell -grayscale -depth 16 -bkgd 777"),
+    ("rgba16_model_gamma_falls_back", 200, 200, RGBA, 16, 420, 420, "-filter mitchell -depth 16 -bkgd 369 -cs gamma1.8"),
 ]
 
 
@@ -52,6 +58,9 @@ def _rows_with_transparency(prod, cfg, seed=3):
     px = rows[:, : cfg.in_w * nch * bps].reshape(cfg.in_h, cfg.in_w, nch, bps)
     px[: cfg.in_h // 3, : cfg.in_w // 2, nch - 1, :] = 0
     px[cfg.in_h // 2:, cfg.in_w // 3:, nch - 1, :] = 255
+    # black and saturated colour (exact zeros / ones after the division by alpha), with and without opacity
+    px[cfg.in_h // 4: cfg.in_h // 2, : cfg.in_w // 4, : nch - 1, :] = 0
+    px[cfg.in_h // 2: 3 * cfg.in_h // 4, cfg.in_w // 2:, : nch - 1, :] = 255
     return rows
 
 
