@@ -66,7 +66,16 @@
 #define IWB2_MAX_GU 16           // longest uniform cycle (inputs) the kernels are built for
 
 // pipeline geometry of the general path as a function of the kernel's uniform step (0 = general-only kernel)
-__host__ __device__ constexpr int iwb2_v_g(int step) { return step > 0 ? IWB2_V_G : 2 * IWB2_V_G; }
+// (16-bit input: a shallow ring.  That kernel is bound by its lookups in the 65 536-entry code -> linear table, i.e. by
+// the L1 hit rate of those lookups -- profiles/r2_gather_probe.txt -- and every KB of shared memory not used is L1)
+#ifndef IWB2_V16_G
+#define IWB2_V16_G 4
+#endif
+#ifndef IWB2_V16_NST
+#define IWB2_V16_NST 3
+#endif
+__host__ __device__ constexpr int iwb2_v_g(int step, bool d16 = false) { return d16 ? IWB2_V16_G : (step > 0 ? IWB2_V_G : 2 * IWB2_V_G); }
+__host__ __device__ constexpr int iwb2_v_nst(bool d16 = false) { return d16 ? IWB2_V16_NST : IWB2_V_NST; }
 __host__ __device__ constexpr int iwb2_h_kp(int step) { return step > 0 ? IWB2_H_KP : 2 * IWB2_H_KP; }
 __host__ __device__ constexpr int iwb2_h_nst(int step) { return step > 0 ? IWB2_H_NST : IWB2_H_NST + 1; }
 // resident CTAs per SM the vertical kernel's register allocation aims at: 4 columns x S slots of FP64 accumulators

@@ -91,6 +91,16 @@ __device__ __forceinline__ void s2_decode_part(const Part2 &pt, int id, int lo, 
   }
 }
 
+// 16-bit input: lookups in the code -> linear table keep their lines in L1 as long as possible, the stores of the
+// intermediate do not allocate there
+__device__ __forceinline__ double s2_ldg_keep(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void s2_stg128_stream(float *p, float a, float b, float c, float d) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 // ---------------------------------------------------------------------------------------------------------
 // vertical kernel.  Warp = 128 adjacent byte columns (lane = 4 of them, one 32-bit word per row), strip of
 // output rows; walks the input rows of the strip once.  Loads run ahead of the arithmetic: while row i is
@@ -105,10 +115,10 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, iwb2_v_minb(S))
   constexpr int SS = (S + 1) & ~1;
   // general path: rows per stage, stages.  A general-only kernel (non-integer factors: the whole image takes this
   // path) gets a deeper pipeline than the general parts of a uniform launch (a few border rows).
-  constexpr int G = iwb2_v_g(STEP), NST = IWB2_V_NST;
+  constexpr int G = iwb2_v_g(STEP, D16), NST = iwb2_v_nst(D16);
   constexpr int TW = D16 ? 256 : 128;                           // bytes of a warp's 128 columns in one input row
   constexpr int LUTB = D16 ? 0 : 256 * 16 * 8;                  // shared-memory colour table (8-bit input only)
-  constexpr int STAGE = G * TW + G * SS * 8;                    // bytes: input rows, then weights
+  constexpr int STAGE = (G * TW + G * SS * 8 + 127) & ~127;     // bytes: input rows, then weights
   constexpr int GU = STEP > 0 ? S * STEP : 4, NSTU = IWB2_U_NST;   // uniform path: one cycle per stage
   constexpr int STEPQ = STEP > 0 ? STEP : 1;
   constexpr int STAGE_U = (GU * TW + GU * SS * 8 + 127) & ~127;
@@ -221,7 +231,7 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, iwb2_v_minb(S))
     if (D16) {                                                  // bytes (hi, lo) of sample c -> code -> global table
       const unsigned wv = c < 2 ? x.a : x.b;
       const unsigned code = __byte_perm(wv, 0, (c & 1) ? 0x4423 : 0x4401);
-      return __ldg(p.lut64k + code);
+      return s2_ldg_keep(p.lut64k + code);
     }
     // 8-bit: code * 128 bytes (16 copies of 8 bytes) + lane copy
     const unsigned sh = c == 0 ? (x.a << 7) : (x.a >> (8 * c - 7));
@@ -258,7 +268,9 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, iwb2_v_minb(S))
     for (int c = 0; c < 4; c++) if (IWB2_DEFER_V) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
     if (o >= o0 && o < o1) {                                    // emitted rows are consecutive: outp walks down the plane
       const float f0 = (float)acc[k][0], f1 = (float)acc[k][1], f2 = (float)acc[k][2], f3 = (float)acc[k][3];
-      if (full) {
+      if (full && D16 && SH == 0) {
+        s2_stg128_stream(outp, f0, f1, f2, f3);                 // (keeps the intermediate out of L1: that is the table's)
+      } else if (full) {
         if (SH == 0) {
           *reinterpret_cast<float4 *>(outp) = make_float4(f0, f1, f2, f3);
         } else if (SH == 2) {

@@ -151,10 +151,10 @@ static inline int iwb2_plan_parts(const int *first, const int *last, int n_out, 
 static inline size_t iwb2_v_smem(int S, int step, int nout, bool d16) {
   const int SS = (S + 1) & ~1;
   const size_t tw = d16 ? 256 : 128;
-  const size_t stage = (size_t)iwb2_v_g(step) * tw + (size_t)iwb2_v_g(step) * SS * 8;
+  const size_t stage = ((size_t)iwb2_v_g(step, d16) * tw + (size_t)iwb2_v_g(step, d16) * SS * 8 + 127) & ~(size_t)127;
   const int gu = step > 0 ? S * step : 4;
   const size_t stage_u = ((size_t)gu * tw + (size_t)gu * SS * 8 + 127) & ~(size_t)127;
-  const size_t ring = std::max((size_t)IWB2_V_NST * stage, (size_t)IWB2_U_NST * stage_u);
+  const size_t ring = std::max((size_t)iwb2_v_nst(d16) * stage, (size_t)IWB2_U_NST * stage_u);
   const size_t warp_bytes = (ring + 8 * 8 + 127) & ~(size_t)127;
   return (d16 ? 0 : 256 * 16 * 8) + IWB2_V_WARPS * warp_bytes + (size_t)((nout + 1) & ~1) * 4 + 16 + 16;
 }
