@@ -81,6 +81,24 @@ __host__ __device__ constexpr int iwb2_h_nst(int step) { return step > 0 ? IWB2_
 // resident CTAs per SM the vertical kernel's register allocation aims at: 4 columns x S slots of FP64 accumulators
 // per thread leave room for IWB2_V_MINB CTAs up to 8 slots; enlargements (12 / 16 open windows) get the whole file
 __host__ __device__ constexpr int iwb2_v_minb(int S) { return S <= 8 ? IWB2_V_MINB : 2; }
+// 16-bit input, up to 8 slots: ONE CTA of 16 warps per SM whose shared memory, beside the pipeline rings, holds the first
+// `lut_ns` entries (~14 000) of the 65 536-entry code -> linear table.  Lookups in global memory are bound by the L1 miss
+// path at ~0.9 per clock per SM and a 512 KB table of doubles does not stay in a sectored L1
+// (profiles/r2y_cfg5_v_summary.txt: 6.7 % hits); shared memory serves ~6 per clock (profiles/r2_gather_probe.txt): every
+// code found there is a request less on the slow path.  The budget stops at 188 KB: the L1 that remains also tracks the
+// misses in flight, and with the last 32 KB handed to the table the kernel is 40 % SLOWER (measured on cfg5: vertical
+// pass 4.85 ms without a shared table, 4.19 ms with 16 warps / 188 KB, 4.33 ms / 150 KB, 5.98 ms / 220 KB, 4.58 ms with
+// 12 warps, 4.49 ms with 8).  Enlargements with 12 / 16 slots need the whole register file per thread and keep the
+// 4-warp layout without a shared table.
+__host__ __device__ constexpr bool iwb2_v16_shared_table(int S, bool d16) { return d16 && S <= 8; }
+#ifndef IWB2_V16_WARPS
+#define IWB2_V16_WARPS 16
+#endif
+#ifndef IWB2_V16_BUDGET_KB
+#define IWB2_V16_BUDGET_KB 188
+#endif
+__host__ __device__ constexpr int iwb2_v_warps(int S, bool d16) { return iwb2_v16_shared_table(S, d16) ? IWB2_V16_WARPS : IWB2_V_WARPS; }
+__host__ __device__ constexpr int iwb2_v_minb2(int S, bool d16) { return iwb2_v16_shared_table(S, d16) ? 1 : iwb2_v_minb(S); }
 
 struct Sched2 {                  // device pointers
   const double *w;               // row r at w + r*SS, r in [-IWB2_WPAD, n_in + IWB2_WPAD); SS = S rounded up to even
@@ -116,7 +134,8 @@ struct V2Params {
   size_t bpr;                    // multiple of 16
   int ncols;                     // sample columns (= in_w * channels)
   const double *lut16;           // 8-bit input: [256][16] code -> linear, every entry repeated 16 times (the shared-memory layout)
-  const double *lut64k;          // 16-bit input: [65536] code -> linear (stays in global memory)
+  const double *lut64k;          // 16-bit input: [65536] code -> linear (global memory; entries below lut_ns also in shared memory)
+  int lut_ns;
   int depth16;                   // samples are 16-bit big-endian
   Sched2 sc;
   float *inter;                  // row-major FP32 intermediate

@@ -110,14 +110,13 @@ __device__ __forceinline__ void s2_stg128_stream(float *p, float a, float b, flo
 // linear table has 65 536 entries: it stays in global memory (L2-resident, read-only path) instead of being
 // replicated in shared memory.
 template <int S, int STEP, int SH, bool D16>
-__global__ void __launch_bounds__(32 * IWB2_V_WARPS, iwb2_v_minb(S))
+__global__ void __launch_bounds__(32 * iwb2_v_warps(S, D16), iwb2_v_minb2(S, D16))
     iwb_v2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_u, const V2Params p) {
   constexpr int SS = (S + 1) & ~1;
   // general path: rows per stage, stages.  A general-only kernel (non-integer factors: the whole image takes this
   // path) gets a deeper pipeline than the general parts of a uniform launch (a few border rows).
   constexpr int G = iwb2_v_g(STEP, D16), NST = iwb2_v_nst(D16);
   constexpr int TW = D16 ? 256 : 128;                           // bytes of a warp's 128 columns in one input row
-  constexpr int LUTB = D16 ? 0 : 256 * 16 * 8;                  // shared-memory colour table (8-bit input only)
   constexpr int STAGE = (G * TW + G * SS * 8 + 127) & ~127;     // bytes: input rows, then weights
   constexpr int GU = STEP > 0 ? S * STEP : 4, NSTU = IWB2_U_NST;   // uniform path: one cycle per stage
   constexpr int STEPQ = STEP > 0 ? STEP : 1;
@@ -133,11 +132,15 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, iwb2_v_minb(S))
   s2_decode_part(p.part, blockIdx.y, p.row_lo, p.row_hi, &o0, &o1, &uni);
   if (STEP == 0) uni = false;
 
-  double *lut_s = (double *)smem_raw;                           // [256][16]
+  constexpr int NWARPS = iwb2_v_warps(S, D16);
+  constexpr bool TAB16 = iwb2_v16_shared_table(S, D16);
+  // shared-memory colour table: 8-bit input [256][16]; 16-bit input (12-warp layout) the first lut_ns entries (a multiple of 16)
+  const int LUTB = D16 ? (TAB16 ? p.lut_ns * 8 : 0) : 256 * 16 * 8;
+  double *lut_s = (double *)smem_raw;
   unsigned char *wbase = smem_raw + LUTB + (size_t)warp * WARP_BYTES;
   const unsigned bar0 = s2_addr(wbase + RING);
-  int *last_s = (int *)(smem_raw + LUTB + (size_t)IWB2_V_WARPS * WARP_BYTES);   // general path: [nout]
-  const int wcol0 = (blockIdx.x * IWB2_V_WARPS + warp) * 128;
+  int *last_s = (int *)(smem_raw + LUTB + (size_t)NWARPS * WARP_BYTES);   // general path: [nout]
+  const int wcol0 = (blockIdx.x * NWARPS + warp) * 128;
   const bool active = wcol0 < p.ncols;
   const unsigned ring0 = s2_addr(wbase);
   const int col0 = wcol0 + lane * 4;
@@ -206,6 +209,9 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, iwb2_v_minb(S))
   }
   if (!uni)
     for (int i = threadIdx.x; i < nout; i += blockDim.x) last_s[i] = p.sc.last[ob + i] - r0;
+  if (TAB16)
+    for (int i = threadIdx.x; i < p.lut_ns / 2; i += blockDim.x)
+      reinterpret_cast<double2 *>(lut_s)[i] = __ldg(reinterpret_cast<const double2 *>(p.lut64k) + i);
   __syncthreads();
   if (!active) return;
   if (!D16) s2_mbar_wait(s2_addr(lbar), 0);
@@ -231,6 +237,12 @@ __global__ void __launch_bounds__(32 * IWB2_V_WARPS, iwb2_v_minb(S))
     if (D16) {                                                  // bytes (hi, lo) of sample c -> code -> global table
       const unsigned wv = c < 2 ? x.a : x.b;
       const unsigned code = __byte_perm(wv, 0, (c & 1) ? 0x4423 : 0x4401);
+      if (TAB16) {                                              // (both loads predicated; no branch)
+        double v = 0.0;
+        if (code < (unsigned)p.lut_ns) v = lut_s[code];
+        else v = s2_ldg_keep(p.lut64k + code);
+        return v;
+      }
       return s2_ldg_keep(p.lut64k + code);
     }
     // 8-bit: code * 128 bytes (16 copies of 8 bytes) + lane copy

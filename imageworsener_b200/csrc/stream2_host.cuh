@@ -148,7 +148,7 @@ static inline int iwb2_plan_parts(const int *first, const int *last, int n_out, 
   return step;
 }
 
-static inline size_t iwb2_v_smem(int S, int step, int nout, bool d16) {
+static inline size_t iwb2_v_smem(int S, int step, int nout, bool d16, int lut_ns = 0) {
   const int SS = (S + 1) & ~1;
   const size_t tw = d16 ? 256 : 128;
   const size_t stage = ((size_t)iwb2_v_g(step, d16) * tw + (size_t)iwb2_v_g(step, d16) * SS * 8 + 127) & ~(size_t)127;
@@ -156,7 +156,16 @@ static inline size_t iwb2_v_smem(int S, int step, int nout, bool d16) {
   const size_t stage_u = ((size_t)gu * tw + (size_t)gu * SS * 8 + 127) & ~(size_t)127;
   const size_t ring = std::max((size_t)iwb2_v_nst(d16) * stage, (size_t)IWB2_U_NST * stage_u);
   const size_t warp_bytes = (ring + 8 * 8 + 127) & ~(size_t)127;
-  return (d16 ? 0 : 256 * 16 * 8) + IWB2_V_WARPS * warp_bytes + (size_t)((nout + 1) & ~1) * 4 + 16 + 16;
+  return (d16 ? (size_t)lut_ns * 8 : 256 * 16 * 8) + iwb2_v_warps(S, d16) * warp_bytes + (size_t)((nout + 1) & ~1) * 4 + 16 + 16;
+}
+// 16-bit input, 12-warp layout: how many table entries fit beside the rings (a multiple of 16; the launch may use up to
+// 220 KB of dynamic shared memory, see iwb2_ctas_per_sm)
+static inline int iwb2_v16_table_entries(int S, int step, int nout) {
+  if (!iwb2_v16_shared_table(S, true)) return 0;
+  const size_t base = iwb2_v_smem(S, step, nout, true, 0);
+  const size_t budget = (size_t)IWB2_V16_BUDGET_KB * 1024;
+  if (base + 16 * 8 > budget) return 0;
+  return (int)std::min<size_t>(65536, ((budget - base) / 8) & ~(size_t)15);
 }
 static inline size_t iwb2_h_smem(int S, int step, int nch, int ntab, int nout) {
   const int SS = (S + 1) & ~1;

@@ -125,3 +125,98 @@ def test_fp32_intermediate_is_bit_identical_to_oracle(prod, oracle_port, case):
     bad = np.argwhere(want.view(np.uint32) != got.view(np.uint32))
     detail = "; ".join(f"(row {j}, col {i}): oracle {want[j, i]!r} cuda {got[j, i]!r}" for j, i in bad[:6])
     assert len(bad) == 0, f"{len(bad)} of {got.size} FP32 intermediate samples differ: {detail}"
+
+
+# ---- the same comparison against the UNMODIFIED reference build --------------------------------------------------
+# The reference does not expose its intermediate, but every allocation it makes goes through the context's
+# mallocfn / freefn (src/imagew.h:467-491).  A freefn that copies the block of in_w * out_h floats just before the
+# reference frees it at the end of iw_process_internal (src/imagew-main.c:1446) captures `intermediate32` as the last
+# processed channel left it -- so the oracle port is not the only witness of the FP32 planes.
+_MALLOCFN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t)
+_FREEFN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+
+
+class _InitParams(C.Structure):
+    _fields_ = [("api_version", C.c_int), ("userdata", C.c_void_p), ("mallocfn", _MALLOCFN), ("freefn", _FREEFN)]
+
+
+def _reference_intermediate(ref, cfg, rows):
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    libc.calloc.restype = C.c_void_p
+    libc.calloc.argtypes = [C.c_size_t, C.c_size_t]
+    libc.free.argtypes = [C.c_void_p]
+    sizes, snaps = {}, []
+    want_bytes = cfg.in_w * cfg.out_h * 4
+
+    def mallocfn(_ud, flags, n):
+        p = libc.calloc(1, n) if flags & 1 else libc.malloc(n)
+        if p:
+            sizes[p] = n
+        return p
+
+    def freefn(_ud, p):
+        if p and sizes.pop(p, None) == want_bytes:
+            snaps.append(np.frombuffer(C.string_at(p, want_bytes), dtype=np.float32).reshape(cfg.out_h, cfg.in_w).copy())
+        libc.free(p)
+
+    params = _InitParams(0, None, _MALLOCFN(mallocfn), _FREEFN(freefn))
+    ctx = ref.iw_create_context(C.cast(C.byref(params), C.c_void_p))
+    assert ctx
+    nch = L.imgtype_num_channels(cfg.imgtype)
+    ref.set_input_from_numpy(ctx, rows[:, : cfg.in_w * nch * (cfg.bit_depth // 8)], cfg.imgtype, cfg.bit_depth, cfg.in_w, cfg.in_h)
+    cfg.apply(ref, ctx)
+    assert ref.iw_process_image(ctx), ref.errmsg(ctx)
+    _, out = ref.get_output_numpy(ctx)
+    out = out.copy()
+    ref.iw_destroy_context(ctx)
+    # (intermediate32 is the first block of that size to be freed: src/imagew-main.c:1446-1448)
+    assert len(snaps) >= 1, "the reference freed no block of the intermediate's size"
+    return snaps[0], out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("down2_lanczos_rgb", "odd_catrom_gray", "up_mitchell_rgb", "gray16_stream",
+                                                            "down3_catrom_holes", "rgba16_up_gather")], ids=lambda c: c[0])
+def test_fp32_intermediate_is_bit_identical_to_the_reference_build(prod, ref, case):
+    name, iw, ih, typ, depth, ow, oh, extra, opts = case
+    cfg = configs.Config(name, iw, ih, typ, depth, ow, oh, f"-width {ow} -height {oh} {extra}")
+    rows = configs.synth_rows(prod, cfg)
+    want, ref_out = _reference_intermediate(ref, cfg, rows)
+
+    dll = prod.dll
+    _job_api(dll)
+    ctx = prod.iw_create_context(None)
+    prod.set_input_from_numpy(ctx, rows, cfg.imgtype, cfg.bit_depth, cfg.in_w, cfg.in_h)
+    cfg.apply(prod, ctx)
+    job = dll.iwb200_job_create(ctx, 0)
+    assert job, prod.errmsg(ctx)
+    info = Info()
+    dll.iwb200_job_get_info(job, C.byref(info))
+    out = np.zeros((oh, info.out_bpr), np.uint8)
+    src = np.ascontiguousarray(rows)
+    assert dll.iwb200_job_run_host(job, src.ctypes.data, src.strides[0], out.ctypes.data, out.strides[0], 0, oh)
+    r0, nr, w = C.c_int(), C.c_int(), C.c_int()
+    got = np.zeros((oh, iw), np.float32)
+    assert dll.iwb200_job_read_intermediate(job, -1, got.ctypes.data, got.size, C.byref(r0), C.byref(nr), C.byref(w))
+    dll.iwb200_job_destroy(job)
+    prod.iw_destroy_context(ctx)
+    assert np.array_equal(out, ref_out)
+    bad = int(np.count_nonzero(want.view(np.uint32) != got.view(np.uint32)))
+    assert bad == 0, f"{bad} of {got.size} FP32 intermediate samples differ from the reference build's"
+
+
+def test_reference_intermediate_snapshot_agrees_with_the_oracle_port(ref, oracle_port):
+    """Host-only: the freefn snapshot of the real reference equals the plane the C restatement keeps."""
+    from oracle_port import OraclePort
+    cfg = configs.Config("snap", 96, 64, RGB, 8, 40, 30, "-width 40 -height 30 -filter lanczos -dither o")
+    rng = np.random.default_rng(5)
+    rows = rng.integers(0, 256, (cfg.in_h, cfg.in_w * 3), dtype=np.uint8)
+    want, _ = _reference_intermediate(ref, cfg, rows)
+    olib = OraclePort()
+    octx = olib.iw_create_context(None)
+    olib.set_input_from_numpy(octx, rows, cfg.imgtype, cfg.bit_depth, cfg.in_w, cfg.in_h)
+    cfg.apply(olib, octx)
+    assert olib.iw_process_image(octx)
+    assert np.array_equal(olib.intermediate(octx).view(np.uint32), want.view(np.uint32))
