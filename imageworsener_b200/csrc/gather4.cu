@@ -29,22 +29,39 @@ bool g4_inter_map(const GHParams &p, int box_cols, CUtensorMap *tm) {
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// How many parts to cut one dimension into, given the CTAs the other dimension contributes per part and the CTAs the
+// device holds at once: about `target_waves` waves, and among the candidates the count whose last wave is fullest.
+static int g4_pick_parts(int slots, int per_part, int total_len, int min_len, double target_waves) {
+  const int nmax = std::max(1, total_len / std::max(1, min_len));            // parts of at least min_len
+  const int want = std::min(nmax, std::max(1, (int)(target_waves * slots) / std::max(1, per_part)));
+  int best = want;
+  double best_eff = -1.0;
+  for (int n = std::max(1, want / 2); n <= std::min(nmax, want + want / 2 + 1); n++) {
+    const double waves = (double)n * per_part / slots;
+    const double eff = waves / std::ceil(waves) - 0.01 * std::abs(n - want) / want;
+    if (eff > best_eff) { best_eff = eff; best = n; }
+  }
+  return best;
+}
+
 template <int W, bool D16, int NCHP>
 bool run_v(const GVJob &job, cudaStream_t st) {
   GVParams p = job.p;
   const int threads = 32 * IWG_WARPS;
   const int colblocks = (p.ncols + 128 * IWG_WARPS - 1) / (128 * IWG_WARPS);
-  // strips: enough CTAs for ~2 waves at 4 CTAs per SM, but at least 64 output rows (a strip re-reads W input rows)
   const int rows = p.row_hi - p.row_lo;
-  const int want = std::max(1, (8 * iwb2_sm_count()) / colblocks);
-  int strip = std::max(64, (rows + want - 1) / want);
+  const size_t tw = D16 ? 256 : 128;
+  const size_t smem_fixed = (D16 ? 0 : 2 * 256 * 8) + (size_t)IWG_WARPS * (IWG_V_NST * IWG_V_G * tw + 128) + 16;
+  auto kernel = iwg_v<W, D16, NCHP>;
+  // strips of output rows: about two waves of CTAs with a full last wave, at least 64 rows each (a strip re-reads W input rows)
+  const int slots = iwb2_ctas_per_sm(kernel, threads, smem_fixed + 4 * 256) * iwb2_sm_count();
+  const int nstrips = g4_pick_parts(slots, colblocks, rows, 64, 2.0);
+  int strip = std::max(64, (rows + nstrips - 1) / nstrips);
   strip = std::min(strip, 2048);
   p.strip = strip;
-  const size_t tw = D16 ? 256 : 128;
-  const size_t smem = (D16 ? 0 : 2 * 256 * 8) + (size_t)IWG_WARPS * (IWG_V_NST * IWG_V_G * tw + 128) + (size_t)strip * 4 + 16;
+  const size_t smem = smem_fixed + (size_t)strip * 4;
   CUtensorMap tm;
   if (!g4_input_map(p, D16, &tm)) return false;
-  auto kernel = iwg_v<W, D16, NCHP>;
   iwb2_ctas_per_sm(kernel, threads, smem);
   kernel<<<dim3((unsigned)colblocks, (unsigned)((rows + strip - 1) / strip)), threads, smem, st>>>(tm, p);
   return true;
@@ -61,17 +78,9 @@ bool run_h(const GHJob &job, cudaStream_t st) {
   const size_t stage = ((size_t)32 * TP * 4 + 127) & ~(size_t)127;
   const size_t smem_fixed = (size_t)NW * (NST * stage + 32 * IWG_OST_PITCH + 128) + (FAST == 2 ? IWB_EST_NREC * sizeof(IwbEstRec) : 0) + 16;
   auto kernel = iwg_h<W, NCH, NCO, FAST>;
-  // column segments: about 2-3 waves of CTAs, and among the candidates the count whose last wave is fullest
+  // column segments: about 2.5 waves of CTAs with a full last wave
   const int slots = iwb2_ctas_per_sm(kernel, threads, smem_fixed + 4 * 512) * iwb2_sm_count();
-  const int want = std::max(1, (5 * slots / 2) / rowblocks);
-  int best = 1;
-  double best_eff = 0.0;
-  for (int n = std::max(1, want / 2); n <= want + want / 2 + 1; n++) {
-    if ((p.out_w + n - 1) / n < 64 && n > 1) break;
-    const double waves = (double)n * rowblocks / slots;
-    const double eff = waves / std::ceil(waves) - 0.01 * std::abs(n - want) / want;
-    if (eff > best_eff) { best_eff = eff; best = n; }
-  }
+  const int best = g4_pick_parts(slots, rowblocks, p.out_w, 64, 2.5);
   int seg = std::max(64, (p.out_w + best - 1) / best);
   seg = std::min((seg + 3) & ~3, 4096);
   p.seg = seg;
