@@ -289,14 +289,14 @@ def known_answers():
         return {}
 
 
-def measure_config_brief(lib, name, device, steps=5, warmup=3, e2e_steps=2, options=None):
+def measure_config_brief(lib, name, device, steps=5, warmup=3, e2e_steps=2, options=None, zoneplate=False):
     """One other BASELINE configuration on one GPU: device-resident ms per image (CUDA events on the launching stream,
     L2 defeated by buffer rotation or by the image size itself), end to end through iw_process_image on host buffers,
     the whole-step roofline fraction, and the FNV-1a-64 of the output against the reference's recorded fingerprint."""
     import torch
     dll = lib.dll
     cfg = configs.get(name)
-    rows = configs.synth_rows(lib, cfg)
+    rows = configs.zoneplate_rows(cfg) if zoneplate else configs.synth_rows(lib, cfg)
     opts = {"cuda:device": device, **(options or {})}
     ctx = make_ctx(lib, cfg, rows=None, options=opts)
     job = dll.iwb200_job_create(ctx, device)
@@ -335,6 +335,8 @@ def measure_config_brief(lib, name, device, steps=5, warmup=3, e2e_steps=2, opti
     lib.iw_destroy_context(ctx)
     del d_in, d_out
     torch.cuda.empty_cache()
+    if zoneplate:      # device time on an image-like input only (no recorded fingerprint, same bytes over PCIe)
+        return {"device_ms": dev_ms, "device_mpix_s": cfg.out_mpix / (dev_ms / 1000.0), "input": "1024 x 1024 zone plate per channel, tiled"}
 
     def e2e_once():
         c = make_ctx(lib, cfg, rows=rows, options=opts)
@@ -725,6 +727,13 @@ def main():
                     other[nm] = measure_config_brief(lib, nm, local_rank)
                 except SystemExit as e:  # noqa: PERF203
                     other[nm] = {"error": str(e)}
+            # the same kernels on an image-like input (noise is the worst case for every table lookup and
+            # clips after filters with negative lobes); device time only
+            for nm in ("cfg2", "cfg3", "cfg5"):
+                try:
+                    other[nm + "_zoneplate"] = measure_config_brief(lib, nm, local_rank, zoneplate=True)
+                except SystemExit as e:  # noqa: PERF203
+                    other[nm + "_zoneplate"] = {"error": str(e)}
         else:
             bands_block = measure_bands(lib, "cfg5", rank, local_rank, world, dist)
         batch_block = {nm: measure_batch(lib, nm, rank, local_rank, world, dist if world > 1 else None) for nm in ("cfg4auto", "cfg4box")}
