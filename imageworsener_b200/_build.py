@@ -22,7 +22,7 @@ EMU_SO = os.path.join(EMU_DIR, "libimagew_emu.so")
 
 HOST_SOURCES = ["api.cpp", "plan.cpp", "weights.cpp", "tables.cpp", "process.cpp", "optimize.cpp", "util.cpp", "estimate.cpp"]
 DEVICE_SOURCES = ["pipeline.cu", "stream2_v.cu", "stream2_v16.cu", "stream2_h1.cu", "stream2_h2.cu", "stream2_h3.cu", "stream2_h4.cu",
-                  "gather4.cu", "stream3_e1.cu", "stream3_e2.cu", "stream3_e3.cu", "stream3_e4.cu"]
+                  "gather4.cu", "gather5.cu", "stream3_e1.cu", "stream3_e2.cu", "stream3_e3.cu", "stream3_e4.cu"]
 OBJ_DIR = os.path.join(HERE, "_obj")
 
 

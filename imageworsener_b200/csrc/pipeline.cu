@@ -26,6 +26,7 @@
 #include "stream2.cuh"
 #include "stream3.cuh"
 #include "gather4.cuh"
+#include "gather5.cuh"
 #include "errdiff.cuh"
 #endif
 
@@ -297,6 +298,9 @@ struct iwb200_job {
     size_t pitch = 0;
     const IwbEstRec *est = nullptr;               // level model of the colour channels' table (estimate.h), 16-bit output
     double est_margin = 0.0;
+    int tile = 0;                                 // windows longer than gather4's register windows: the tile kernels (gather5.cu)
+    int tile_max_nb = 0;
+    const DevCommon *cm_g = nullptr;
   } gather;
   std::vector<std::unique_ptr<VH3State>> vh3;    // fused-kernel state per row range (stream3.cuh)
   int gen3 = 0;                                 // the fused kernel is opt-in (cuda:gen=3): 0 never, 2 whenever supported
@@ -1159,7 +1163,17 @@ static void gather_plan_build(iwb200_job *job) {
     return (m + 1) & ~1;
   };
   g.WV = width_of(hv); g.WH = width_of(hh);
-  if (!iwg_supported(g.WV, g.WH, nch)) return;
+  g.tile = 0;
+  if (!iwg_supported(g.WV, g.WH, nch)) {
+    // longer windows (reductions beyond 2x, Lanczos3): the tile kernels, which have no random dither
+    if (!iwt_supported(g.WV, g.WH, nch) || job->any_random) return;
+    g.tile = 1;
+    g.tile_max_nb = 0;
+    const int ow = (int)hh.first.size();
+    for (int s0 = 0; s0 < ow; s0 += 32) g.tile_max_nb = std::max(g.tile_max_nb, hh.first[std::min(s0 + 32, ow) - 1] + g.WH - hh.first[s0]);
+    g.cm_g = job->upload(&job->cm, 1);
+    if (!g.cm_g) return;
+  }
   g.nco = ctx->out_nch;
   for (int k = 0; k < g.nco; k++) {
     int src = -1;
@@ -1228,7 +1242,9 @@ static bool gather_run(iwb200_job *job, const DevInput &in, const DevOutput &out
     vj.W = g.WV; vj.nchp = nch;
     {
       prof_scope ps(job, 5, stream);
-      if (!iwg_run_v(vj, (cudaStream_t)stream)) return fail(job, "gather path: no vertical kernel variant");
+      if (g.tile) job->last_gen = 5;
+      if (!(g.tile ? iwt_run_v(vj, g.vfirst.data(), (cudaStream_t)stream) : iwg_run_v(vj, (cudaStream_t)stream)))
+        return fail(job, "gather path: no vertical kernel variant");
       g_launches++;
     }
     GHJob hj{};
@@ -1243,7 +1259,8 @@ static bool gather_run(iwb200_job *job, const DevInput &in, const DevOutput &out
     hj.W = g.WH; hj.nch = nch; hj.nco = g.nco;
     {
       prof_scope ps(job, 1, stream);
-      if (!iwg_run_h(hj, (cudaStream_t)stream)) return fail(job, "gather path: no horizontal kernel variant");
+      if (!(g.tile ? iwt_run_h(hj, g.cm_g, g.tile_max_nb, (cudaStream_t)stream) : iwg_run_h(hj, (cudaStream_t)stream)))
+        return fail(job, "gather path: no horizontal kernel variant");
       g_launches++;
     }
     if (job->negate || job->clear_transparent) {
@@ -1590,7 +1607,7 @@ static iwb200_job *job_build(iw_context *ctx, int device) {
     const char *og = iwb_option(ctx, "cuda:gather");
     if (!job->fused.enabled && !(og && !strcmp(og, "0"))) gather_plan_build(job);
   }
-  info.uses_fused_kernel = job->fused.enabled ? (job->fused.v2 ? 2 : 1) : (job->gather.enabled ? 4 : 0);
+  info.uses_fused_kernel = job->fused.enabled ? (job->fused.v2 ? 2 : 1) : (job->gather.enabled ? (job->gather.tile ? 5 : 4) : 0);
 #endif
   job->flush_tables();
   return job;

@@ -44,6 +44,26 @@ SHAPES = [
 ]
 
 
+# windows of more than 8 taps: the tile kernels (csrc/gather5.cu)
+TILE_SHAPES = [
+    ("t_rgba8_thumb_auto", 480, 270, RGBA, 8, 64, 36, ""),
+    ("t_rgba8_down2_lanczos", 400, 300, RGBA, 8, 200, 150, "-filter lanczos"),
+    ("t_rgba8_down3_catrom_bkgd", 600, 420, RGBA, 8, 200, 140, "-filter catrom -bkgd 3a7"),
+    ("t_rgba16_down25_mitchell_16", 500, 375, RGBA, 16, 200, 150, "-filter mitchell -depth 16 -bkgd 123"),
+    ("t_rgba16_down4_lanczos_o", 640, 480, RGBA, 16, 160, 120, "-filter lanczos -dither o"),
+    ("t_ga8_down5_keepalpha", 500, 400, GA, 8, 100, 80, "-filter catrom -grayscale"),
+    ("t_ga16_down3_halftone", 420, 300, GA, 16, 140, 100, "-filter lanczos2 -grayscale -bkgd 888 -dither halftone"),
+    ("t_rgba8_checker", 512, 384, RGBA, 8, 150, 113, "-filter mitchell -bkgd e42,0f5 -checkersize 9"),
+    ("t_rgba8_translucent", 512, 384, RGBA, 8, 170, 128, "-filter catrom -bkgd 00ff5550"),
+    ("t_rgba8_aniso", 512, 200, RGBA, 8, 100, 190, "-filter lanczos"),
+    ("t_rgba8_crop_cc", 512, 384, RGBA, 8, 120, 90, "-filter catrom -crop 17,9,400,300 -cc 6 -dither o"),
+    ("t_rgba8_intclamp", 400, 300, RGBA, 8, 130, 100, "-filter lanczos -intclamp"),
+    ("t_rgba8_up_lanczos3x", 60, 40, RGBA, 8, 300, 200, "-filter lanczos"),
+    ("t_rgba8_down12_box", 1200, 900, RGBA, 8, 100, 75, "-filter box"),
+    ("t_rgba8_ragged", 333, 257, RGBA, 8, 77, 61, "-filter catrom -bkgd fff"),
+]
+
+
 def _cfg(shape):
     name, iw, ih, typ, depth, ow, oh, extra = shape
     return configs.Config(name, iw, ih, typ, depth, ow, oh, f"-width {ow} -height {oh} {extra}")
@@ -65,7 +85,7 @@ def _rows_with_transparency(prod, cfg, seed=3):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", SHAPES, ids=[s[0] for s in SHAPES])
+@pytest.mark.parametrize("shape", SHAPES + TILE_SHAPES, ids=[s[0] for s in SHAPES + TILE_SHAPES])
 def test_gather_path_matches_reference(prod, ref, shape):
     cfg = _cfg(shape)
     rows = _rows_with_transparency(prod, cfg)
@@ -100,7 +120,27 @@ def test_these_jobs_are_planned_onto_the_gather_kernels(prod, shape):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[3], SHAPES[7]], ids=lambda s: s[0])
+@pytest.mark.parametrize("shape", TILE_SHAPES[:12], ids=[s[0] for s in TILE_SHAPES[:12]])
+def test_these_jobs_are_planned_onto_the_tile_kernels(prod, shape):
+    from test_intermediate import Info, _job_api
+    cfg = _cfg(shape)
+    rows = configs.synth_rows(prod, cfg)
+    dll = prod.dll
+    _job_api(dll)
+    ctx = prod.iw_create_context(None)
+    prod.set_input_from_numpy(ctx, rows, cfg.imgtype, cfg.bit_depth, cfg.in_w, cfg.in_h)
+    cfg.apply(prod, ctx)
+    job = dll.iwb200_job_create(ctx, 0)
+    assert job, prod.errmsg(ctx)
+    info = Info()
+    dll.iwb200_job_get_info(job, C.byref(info))
+    dll.iwb200_job_destroy(job)
+    prod.iw_destroy_context(ctx)
+    assert info.uses_fused_kernel == 5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[3], SHAPES[7], TILE_SHAPES[0], TILE_SHAPES[3], TILE_SHAPES[5]], ids=lambda s: s[0])
 @pytest.mark.parametrize("nbands", [2, 5])
 def test_gather_path_bands_concatenate_to_reference(prod, ref, shape, nbands):
     cfg = _cfg(shape)

@@ -22,6 +22,8 @@ CASES = [
     ("down2_lanczos_rgb_gen3", 512, 384, RGB, 8, 256, 192, "-filter lanczos -dither o", {"cuda:gen": 3}),
     ("rgba16_up_gather", 200, 150, L.IW_IMGTYPE_RGBA, 16, 500, 380, "-filter mitchell -bkgd 369", {}),
     ("ga8_down_gather", 400, 300, L.IW_IMGTYPE_GRAYA, 8, 260, 200, "-filter catrom", {}),
+    ("rgba8_down3_tile", 420, 300, L.IW_IMGTYPE_RGBA, 8, 140, 100, "-filter catrom -bkgd 246", {}),
+    ("ga16_down4_tile", 400, 320, L.IW_IMGTYPE_GRAYA, 16, 100, 80, "-filter lanczos", {}),
     ("down2_catrom_gray_gen3", 1002, 702, GRAY, 8, 501, 351, "-filter catrom -grayscale -dither r", {"cuda:gen": 3}),
     ("odd_catrom_gray", 500, 333, GRAY, 8, 217, 140, "-filter catrom -dither r", {}),
     ("up_mitchell_rgb", 200, 150, RGB, 8, 320, 260, "-filter mitchell", {}),
