@@ -87,7 +87,7 @@ def main():
         nch = 4 if seed % 3 else 2
         depth = 16 if seed % 4 else 8
         iw, ih = int(r.integers(40, 400)), int(r.integers(40, 300))
-        f = float(r.choice([0.55, 0.8, 1.0, 1.5, 2.0, 3.0, 4.0])) * float(r.uniform(0.97, 1.03))
+        f = float(r.choice([0.13, 0.25, 0.4, 0.55, 0.8, 1.0, 1.5, 2.0, 3.0, 4.0])) * float(r.uniform(0.97, 1.03))
         ow, oh = max(8, int(iw * f)), max(8, int(ih * f * float(r.uniform(0.9, 1.1))))
         out16 = seed % 5 != 0
         bk = "%02x%02x%02x" % tuple(int(v) for v in r.integers(0, 256, 3))
@@ -122,7 +122,7 @@ def main():
         if nd:
             bada += 1
             print(f"DIFFALPHA seed {seed} {cfg.args!r} {iw}x{ih} depth {depth} nch {nch}: {nd} bytes", flush=True)
-    print(f"images with alpha (gather-form kernels, level model): {n} cases, {samplesa} output bytes compared, {bada} cases differ", flush=True)
+    print(f"images with alpha (gather-form and tile kernels, level model): {n} cases, {samplesa} output bytes compared, {bada} cases differ", flush=True)
     bad += bada
     big = 0
     for dither in ("-dither o", "-dither r", "", "-dither halftone"):
