@@ -43,13 +43,14 @@ FP64_PEAK_SOURCE = "builder-measured (tools/fp64_peak.cu, profiles/r1_fp64_peak.
 
 
 def kernel_sources_sha() -> str:
-    """Fingerprint of the device code the library was built from (the ncu capture in profiles/traffic.json is only
-    valid for the kernels it was taken on)."""
+    """Fingerprint of the device code of the headline configuration's kernels (the generation-2 streaming kernels:
+    stream2*.cu/.cuh/.inc and what they include).  The ncu capture in profiles/traffic.json is only valid for the kernels
+    it was taken on."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "imageworsener_b200", "csrc")
     for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh", ".inc")):
+        if f.startswith("stream2") or f in ("kernels.cuh", "prng.cuh"):
             h.update(f.encode())
             h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]

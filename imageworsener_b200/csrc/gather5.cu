@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(32 * IWT_WARPS) iwt_v(const __grid_constant__ 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int o0 = p.row_lo + blockIdx.y * p.strip, o1 = min(o0 + p.strip, p.row_hi);
-  double *lut_c_s = (double *)smem_raw, *lut_a_s = lut_c_s + 256;
+  double *lut_c_s = (double *)smem_raw, *lut_a_s = lut_c_s + 256;      // (NCHP = 0: an image without alpha, one table)
   unsigned char *tile = smem_raw + LUTB + (size_t)warp * tile_rows * TW;
   const unsigned tile0 = s2_addr(tile), bar = s2_addr(smem_raw + LUTB + (size_t)IWT_WARPS * tile_rows * TW) + 8 * warp;
   const int wcol0 = (blockIdx.x * IWT_WARPS + warp) * 128;
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(32 * IWT_WARPS) iwt_v(const __grid_constant__ 
     __syncwarp();
   }
   if (!D16)
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { lut_c_s[i] = p.lut_c[i]; lut_a_s[i] = p.lut_a[i]; }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { lut_c_s[i] = p.lut_c[i]; if (NCHP > 0) lut_a_s[i] = p.lut_a[i]; }
   __syncthreads();
   if (!active) return;
   s2_mbar_wait(bar, 0);
@@ -92,14 +92,14 @@ __global__ void __launch_bounds__(32 * IWT_WARPS) iwt_v(const __grid_constant__ 
       double v[4];
 #pragma unroll
       for (int c = 0; c < 4; c++) {
-        const bool is_alpha = (c % NCHP) == NCHP - 1;
+        const bool is_alpha = NCHP > 0 && (c % (NCHP > 0 ? NCHP : 1)) == NCHP - 1;
         if (D16) v[c] = __ldg((is_alpha ? p.lut_a : p.lut_c) + code[c]);
         else v[c] = (is_alpha ? lut_a_s : lut_c_s)[code[c]];
       }
       // colour x opacity (reference: in_pix[j] *= tmp_alpha, src/imagew-main.c:880-885)
       if (NCHP == 4) {
         v[0] = __dmul_rn(v[0], v[3]); v[1] = __dmul_rn(v[1], v[3]); v[2] = __dmul_rn(v[2], v[3]);
-      } else {
+      } else if (NCHP == 2) {
         v[0] = __dmul_rn(v[0], v[1]); v[2] = __dmul_rn(v[2], v[3]);
       }
 #pragma unroll
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(32 * IWT_WARPS) iwt_h(const GHParams p, const 
   const int b0 = __ldg(p.sc.first + seg0);
   const int nb = __ldg(p.sc.first + seg1 - 1) + W - b0;          // input pixels the segment's windows span (<= max_nb)
   const int mine = (valid ? __ldg(p.sc.first + xo) : b0) - b0;  // this lane's window start within the segment
+  static_assert(NCH >= 1 && NCH <= 4, "channels");
   for (int t = 0; t < W; t++) wts[t * 32 + lane] = valid ? __ldg(p.sc.w + (size_t)xo * W + t) : 0.0;
   const int y0 = p.row_lo + blockIdx.y * rows_per_warp, y1 = min(y0 + rows_per_warp, p.row_hi);
   // the segment's pixels of intermediate row y -> rowbuf[slot], 8 bytes per copy (rows start on 16 bytes, segments of a
@@ -177,8 +178,13 @@ __global__ void __launch_bounds__(32 * IWT_WARPS) iwt_h(const GHParams p, const 
   auto fetch = [&](int y, int slot) {
     const float *src = p.inter + (size_t)(y - p.row_lo) * p.pitch + (size_t)b0 * NCH;
     const unsigned dst = s2_addr(rowbuf + (size_t)slot * rowbuf_floats);
-    for (int i = lane * 2; i < nfl; i += 64)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + i * 4), "l"(src + i) : "memory");
+    if (NCH % 2 == 0) {
+      for (int i = lane * 2; i < nfl; i += 64)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + i * 4), "l"(src + i) : "memory");
+    } else {                                                    // (no alpha: 1 or 3 floats per pixel, segments start on 4 bytes)
+      for (int i = lane; i < nfl; i += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + i * 4), "l"(src + i) : "memory");
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   if (y0 < y1) fetch(y0, 0);
@@ -201,7 +207,11 @@ __global__ void __launch_bounds__(32 * IWT_WARPS) iwt_h(const GHParams p, const 
       const double w = wts[t * 32 + lane];
       float f[NCH];
       if (NCH == 4) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[NCH - 1]) : "r"(px0 + t * 16));
-      else asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(f[0]), "=f"(f[NCH - 1]) : "r"(px0 + t * 8));
+      else if (NCH == 2) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(f[0]), "=f"(f[NCH - 1]) : "r"(px0 + t * 8));
+      else {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) f[c] = s2_ldsf(px0 + (t * NCH + c) * 4);
+      }
       // (a lane whose weight is 0.0 here adds +-0 to a sum that is never -0: bit-identical to skipping the tap; what
       // the buffer holds beyond the row's end is therefore irrelevant as long as it is finite or the product is dropped)
       if (w != 0.0) {
@@ -214,7 +224,7 @@ __global__ void __launch_bounds__(32 * IWT_WARPS) iwt_h(const GHParams p, const 
       for (int c = 0; c < NCH; c++) acc[c] = acc[c] < 0.0 ? 0.0 : (acc[c] > 1.0 ? 1.0 : acc[c]);
     }
     if (valid) {
-      const double a = (double)(float)acc[NCH - 1];             // the resized alpha plane is FP32 (:1057-1061)
+      const double a = NCH % 2 == 0 ? (double)(float)acc[NCH - 1] : 0.0;   // the resized alpha plane is FP32 (:1057-1061); odd NCH: no alpha
       uint8_t *dst = p.out.pix + (size_t)(y - p.out.row_origin) * p.out.bpr + (size_t)xo * bpp;
 #pragma unroll
       for (int k = 0; k < NCO; k++) {
@@ -301,9 +311,10 @@ bool t5_run_h(const GHJob &job, const DevCommon *cm_g, int max_nb, cudaStream_t 
 }  // namespace
 
 bool iwt_supported(int WV, int WH, int nch) {
-  return WV >= 2 && WH >= 2 && WV <= IWT_MAXW && WH <= IWT_MAXW && (nch == 2 || nch == 4) && iwb2_tensor_map_encoder() != nullptr;
+  return WV >= 2 && WH >= 2 && WV <= IWT_MAXW && WH <= IWT_MAXW && nch >= 1 && nch <= 4 && iwb2_tensor_map_encoder() != nullptr;
 }
 bool iwt_run_v(const GVJob &job, const int *first_host, cudaStream_t st) {
+  if (job.nchp == 0) return job.p.depth16 ? t5_run_v<true, 0>(job, first_host, st) : t5_run_v<false, 0>(job, first_host, st);
   if (job.p.depth16) return job.nchp == 4 ? t5_run_v<true, 4>(job, first_host, st) : t5_run_v<true, 2>(job, first_host, st);
   return job.nchp == 4 ? t5_run_v<false, 4>(job, first_host, st) : t5_run_v<false, 2>(job, first_host, st);
 }
@@ -313,6 +324,8 @@ bool iwt_run_h(const GHJob &job, const DevCommon *cm_g, int max_nb, cudaStream_t
     if (job.nco == 3) return t5_run_h<4, 3>(job, cm_g, max_nb, st);
     return false;
   }
+  if (job.nch == 3) return job.nco == 3 ? t5_run_h<3, 3>(job, cm_g, max_nb, st) : false;
+  if (job.nch == 1) return job.nco == 1 ? t5_run_h<1, 1>(job, cm_g, max_nb, st) : false;
   if (job.nco == 2) return t5_run_h<2, 2>(job, cm_g, max_nb, st);
   if (job.nco == 1) return t5_run_h<2, 1>(job, cm_g, max_nb, st);
   return false;

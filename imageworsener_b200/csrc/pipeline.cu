@@ -1123,9 +1123,12 @@ static void gather_plan_build(iwb200_job *job) {
   const int nch = ctx->in_nch_phys;
   if (ctx->img1.sampletype != IW_SAMPLETYPE_UINT || (ctx->img1.bit_depth != 8 && ctx->img1.bit_depth != 16)) return;
   if ((ctx->img1.orient_transform & 7) != 0) return;
-  if (nch != 2 && nch != 4) return;
-  if (ctx->in_type_logical != ctx->img1.imgtype || !job->has_alpha || job->nproc != nch || ctx->mid_nch != nch) return;
-  if (ctx->in_alpha_index != nch - 1) return;
+  // images WITHOUT alpha that the scatter-form kernels do not take (16-bit output, more than 16 open windows) run on the
+  // tile kernels with no premultiplication: gray (1 channel) and RGB (3)
+  const bool noalpha = !job->has_alpha;
+  if (noalpha ? (nch != 1 && nch != 3) : (nch != 2 && nch != 4)) return;
+  if (ctx->in_type_logical != ctx->img1.imgtype || job->nproc != nch || ctx->mid_nch != nch) return;
+  if (!noalpha && ctx->in_alpha_index != nch - 1) return;
   if (ctx->img2.sampletype != IW_SAMPLETYPE_UINT || (ctx->img2.bit_depth != 8 && ctx->img2.bit_depth != 16)) return;
   if (job->any_errdiff) return;
   if (ctx->axis[0].per_channel_tables || ctx->axis[1].per_channel_tables) return;
@@ -1138,10 +1141,14 @@ static void gather_plan_build(iwb200_job *job) {
     if (c < 0 || c >= nch || seen[c] || mc.to_gray) return;
     seen[c] = true;
     const bool is_alpha = mc.channeltype == IW_CHANNELTYPE_ALPHA;
-    if (is_alpha != (c == nch - 1)) return;
+    if (noalpha ? is_alpha : (is_alpha != (c == nch - 1))) return;
     const DevChanIn &ci = job->cin[p];
     if (ci.early_bkgd || !ci.lut[0]) return;
-    if (is_alpha) {
+    if (noalpha) {
+      if (ci.premult || job->cout[p].premult) return;
+      if (lut_c && lut_c != ci.lut[0]) return;
+      lut_c = ci.lut[0];
+    } else if (is_alpha) {
       if (ci.premult) return;
       if (lut_a && lut_a != ci.lut[0]) return;
       lut_a = ci.lut[0];
@@ -1154,7 +1161,7 @@ static void gather_plan_build(iwb200_job *job) {
     g.chan_of_proc[p] = c;
     g.ch[c] = job->cout[p];
   }
-  if (!lut_c || !lut_a) return;
+  if (!lut_c || (!noalpha && !lut_a)) return;
   HostSched hv, hh;
   if (!build_windows(job->vtab[0], &hv) || !build_windows(job->htab[0], &hh)) return;
   auto width_of = [](const HostSched &h) {
@@ -1164,7 +1171,7 @@ static void gather_plan_build(iwb200_job *job) {
   };
   g.WV = width_of(hv); g.WH = width_of(hh);
   g.tile = 0;
-  if (!iwg_supported(g.WV, g.WH, nch)) {
+  if (noalpha || !iwg_supported(g.WV, g.WH, nch)) {
     // longer windows (reductions beyond 2x, Lanczos3): the tile kernels, which have no random dither
     if (!iwt_supported(g.WV, g.WH, nch) || job->any_random) return;
     g.tile = 1;
@@ -1181,7 +1188,7 @@ static void gather_plan_build(iwb200_job *job) {
     if (src != k) return;                                        // (output channel k is interleaved channel k)
     g.out_src[k] = src;
   }
-  if (g.nco != nch && g.nco != nch - 1) return;
+  if (g.nco != nch && (noalpha || g.nco != nch - 1)) return;
   if (!build_gather_sched(job, hv, job->vtab[0], g.WV, &g.sv) || !build_gather_sched(job, hh, job->htab[0], g.WH, &g.sh)) return;
   {
     DevChanOut four[4];
@@ -1239,7 +1246,7 @@ static bool gather_run(iwb200_job *job, const DevInput &in, const DevOutput &out
     vp.tm_rows = job->vtab[0].max_src(c0, c1) - vp.tm_row0 + 1;
     vp.sc = g.sv; vp.inter = g.inter; vp.pitch = (int)g.pitch; vp.row_base = c0; vp.row_lo = c0; vp.row_hi = c1;
     vp.intclamp = job->cm.intclamp;
-    vj.W = g.WV; vj.nchp = nch;
+    vj.W = g.WV; vj.nchp = job->has_alpha ? nch : 0;            // (0: no alpha, nothing to premultiply)
     {
       prof_scope ps(job, 5, stream);
       if (g.tile) job->last_gen = 5;

@@ -61,6 +61,13 @@ TILE_SHAPES = [
     ("t_rgba8_up_lanczos3x", 60, 40, RGBA, 8, 300, 200, "-filter lanczos"),
     ("t_rgba8_down12_box", 1200, 900, RGBA, 8, 100, 75, "-filter box"),
     ("t_rgba8_ragged", 333, 257, RGBA, 8, 77, 61, "-filter catrom -bkgd fff"),
+    # images without alpha that the scatter-form kernels do not take: 16-bit output, more than 16 open windows
+    ("t_rgb16_down2_to16", 400, 300, L.IW_IMGTYPE_RGB, 16, 200, 150, "-filter lanczos -depth 16"),
+    ("t_rgb8_up_to16", 200, 150, L.IW_IMGTYPE_RGB, 8, 500, 377, "-filter mitchell -depth 16"),
+    ("t_gray16_down3_to16", 600, 420, L.IW_IMGTYPE_GRAY, 16, 200, 140, "-filter catrom -grayscale -depth 16"),
+    ("t_gray16_to16_rec709_o", 320, 240, L.IW_IMGTYPE_GRAY, 16, 251, 188, "-filter lanczos2 -grayscale -depth 16 -cs rec709 -dither o"),
+    ("t_rgb8_up8_catrom", 60, 45, L.IW_IMGTYPE_RGB, 8, 480, 360, "-filter catrom -dither o"),
+    ("t_rgb16_depth12", 300, 200, L.IW_IMGTYPE_RGB, 16, 260, 170, "-filter mitchell -depth 12"),
 ]
 
 
@@ -120,7 +127,7 @@ def test_these_jobs_are_planned_onto_the_gather_kernels(prod, shape):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", TILE_SHAPES[:12], ids=[s[0] for s in TILE_SHAPES[:12]])
+@pytest.mark.parametrize("shape", TILE_SHAPES[:12] + TILE_SHAPES[15:], ids=[s[0] for s in TILE_SHAPES[:12] + TILE_SHAPES[15:]])
 def test_these_jobs_are_planned_onto_the_tile_kernels(prod, shape):
     from test_intermediate import Info, _job_api
     cfg = _cfg(shape)

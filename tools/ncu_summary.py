@@ -28,16 +28,12 @@ if '--traffic' in sys.argv:      # record DRAM bytes per launch for bench.py's r
         return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
     tp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles', 'traffic.json')
     d = json.load(open(tp)) if os.path.exists(tp) else {}
-    # the capture is only valid for the kernels it was taken on: stamp it (bench.py prints null when HEAD's differ)
+    # the capture is only valid for the kernels it was taken on: stamp it with bench.py's fingerprint of their sources
+    # (bench.py prints null when HEAD's differ)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
-    import hashlib
-    h = hashlib.sha256()
-    cs = os.path.join(root, 'imageworsener_b200', 'csrc')
-    for f in sorted(os.listdir(cs)):
-        if f.endswith(('.cu', '.cuh', '.inc')):
-            h.update(f.encode()); h.update(open(os.path.join(cs, f), 'rb').read())
-    sha = h.hexdigest()[:16]
+    import bench
+    sha = bench.kernel_sources_sha()
     if d.get('kernel_sources_sha') != sha:
         d = {}
     d['kernel_sources_sha'] = sha
