@@ -301,6 +301,11 @@ struct iwb200_job {
     int tile = 0;                                 // windows longer than gather4's register windows: the tile kernels (gather5.cu)
     int tile_max_nb = 0;
     const DevCommon *cm_g = nullptr;
+    // images without alpha: the vertical pass runs on the scatter-form kernel of stream2.cuh (one table lookup per
+    // sample instead of one per tap) and feeds the tile horizontal kernel
+    int v2 = 0, v2_S = 0;
+    std::vector<int> v2first, v2last;
+    const double *lut16 = nullptr;
   } gather;
   std::vector<std::unique_ptr<VH3State>> vh3;    // fused-kernel state per row range (stream3.cuh)
   int gen3 = 0;                                 // the fused kernel is opt-in (cuda:gen=3): 0 never, 2 whenever supported
@@ -1181,6 +1186,24 @@ static void gather_plan_build(iwb200_job *job) {
     g.cm_g = job->upload(&job->cm, 1);
     if (!g.cm_g) return;
   }
+  g.v2 = 0;
+  if (noalpha && !ctx->intclamp) {
+    HostSched hv2;
+    const char *o = iwb_option(ctx, "cuda:gen");
+    if (!(o && atoi(o) == 1) && build_sched(job->vtab[0], 16, &hv2) && iwb2_v_supported(hv2.S)) {
+      job->s2_store.reset(new iwb200_job::s2_tables());
+      bool ok = upload_sched2(job, hv2, job->in_h, job->out.height, &job->s2_store->v);
+      if (ok && ctx->img1.bit_depth == 8) {
+        std::vector<double> rep(256 * 16);                      // the vertical kernel's shared-memory table, ready to bulk-copy
+        const std::vector<double> &src = job->lut_host[lut_c];
+        ok = src.size() == 256;
+        for (int i = 0; ok && i < 256 * 16; i++) rep[i] = src[i >> 4];
+        g.lut16 = ok ? job->upload(rep.data(), rep.size()) : nullptr;
+        ok = ok && g.lut16 != nullptr;
+      }
+      if (ok) { g.v2 = 1; g.v2_S = hv2.S; g.v2first = hv2.first; g.v2last = hv2.last; }
+    }
+  }
   g.nco = ctx->out_nch;
   for (int k = 0; k < g.nco; k++) {
     int src = -1;
@@ -1247,7 +1270,19 @@ static bool gather_run(iwb200_job *job, const DevInput &in, const DevOutput &out
     vp.sc = g.sv; vp.inter = g.inter; vp.pitch = (int)g.pitch; vp.row_base = c0; vp.row_lo = c0; vp.row_hi = c1;
     vp.intclamp = job->cm.intclamp;
     vj.W = g.WV; vj.nchp = job->has_alpha ? nch : 0;            // (0: no alpha, nothing to premultiply)
-    {
+    if (g.tile && g.v2) {
+      V2Job v2j{};
+      V2Params &v2p = v2j.p;
+      v2p.src = src0; v2p.bpr = in.bpr; v2p.ncols = job->in_w * nch; v2p.lut16 = g.lut16; v2p.lut64k = g.lut_c; v2p.depth16 = g.depth16;
+      v2p.sc = job->s2_store->v;
+      v2p.tm_row0 = g.v2first[c0]; v2p.tm_rows = g.v2last[c1 - 1] - g.v2first[c0] + 1;
+      v2p.inter = g.inter; v2p.pitch = (int)g.pitch; v2p.sh = 0; v2p.row_base = c0; v2p.row_lo = c0; v2p.row_hi = c1;
+      v2j.S = g.v2_S; v2j.first_host = g.v2first.data(); v2j.last_host = g.v2last.data(); v2j.strip_override = 0; v2j.allow_uniform = 1;
+      prof_scope ps(job, 5, stream);
+      job->last_gen = 5;
+      if (!iwb2_run_v(v2j, (cudaStream_t)stream)) return fail(job, "tile path: no vertical kernel variant");
+      g_launches++;
+    } else {
       prof_scope ps(job, 5, stream);
       if (g.tile) job->last_gen = 5;
       if (!(g.tile ? iwt_run_v(vj, g.vfirst.data(), (cudaStream_t)stream) : iwg_run_v(vj, (cudaStream_t)stream)))

@@ -183,5 +183,6 @@ bool iwb2_run_v(const V2Job &job, cudaStream_t st);   // false: no kernel varian
 bool iwb2_run_h(const H2Job &job, cudaStream_t st);
 int iwb2_h_shift(const H2Job &job);                    // the column shift (0..3) this horizontal launch wants from the vertical one
 bool iwb2_supported(int SV, int SH, int nch, int nco, int epi);
+bool iwb2_v_supported(int SV);   // the vertical kernel alone (feeding another horizontal kernel: gather5.cu)
 
 #endif  // !IWB_EMU

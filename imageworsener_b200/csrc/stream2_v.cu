@@ -9,6 +9,8 @@ bool iwb2_supported(int SV, int SH, int nch, int nco, int epi) {
          (epi == 1 || epi == 2 || epi == 3 || epi == 4);
 }
 
+bool iwb2_v_supported(int SV) { return iwb2_s_built(SV) && iwb2_tensor_map_encoder() != nullptr; }
+
 bool iwb2_run_v(const V2Job &job, cudaStream_t st) { return job.p.depth16 ? iwb2_run_v16(job, st) : iwb2_run_v8(job, st); }
 
 static bool run_h_any(const H2Job &job, cudaStream_t st, int *shift_only) {
