@@ -39,6 +39,15 @@
 #ifndef IWB2_H_WARPS
 #define IWB2_H_WARPS 4
 #endif
+#ifndef IWB2_H_MINB
+#define IWB2_H_MINB 0            // resident CTAs per SM the horizontal kernel's register allocation aims at (0: no cap)
+#endif
+#ifndef IWB2_PARTS_FULL
+#define IWB2_PARTS_FULL 1        // the uniform parts of a launch fill the wave by themselves (stream2_host.cuh)
+#endif
+#ifndef IWB2_H_SWAP
+#define IWB2_H_SWAP 1            // horizontal launch order: row blocks fastest, so that the short border parts come last
+#endif
 #ifndef IWB2_H_KP
 #define IWB2_H_KP 4              // general path: pixel columns per stage
 #endif

@@ -490,7 +490,12 @@ __host__ __device__ constexpr int iwb2_tile_pitch(int k) { return (((k + 3) / 4)
 // for grayscale, src/imagew-main.c:1676-1684: three intermediate channels reading the same input channel, so one
 // resampled value serves the three; they differ only in their random-dither draws)
 template <int S, int STEP, int NCH, int EPI, int NCO = NCH>
-__global__ void __launch_bounds__(32 * IWB2_H_WARPS)
+__global__ void
+#if IWB2_H_MINB > 0
+    __launch_bounds__(32 * IWB2_H_WARPS, IWB2_H_MINB)
+#else
+    __launch_bounds__(32 * IWB2_H_WARPS)
+#endif
     iwb_h2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_u, const H2Params p) {
   constexpr int SS = (S + 1) & ~1;
   constexpr bool DEFER = IWB2_DEFER_H && S * NCH <= 24;         // (deferred adds double the accumulator registers)
@@ -512,7 +517,8 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int xo0, xo1;
   bool uni;
-  s2_decode_part(p.part, blockIdx.x, 0, p.out_w, &xo0, &xo1, &uni);
+  const int part_id = IWB2_H_SWAP ? blockIdx.y : blockIdx.x, rowblock = IWB2_H_SWAP ? blockIdx.x : blockIdx.y;
+  s2_decode_part(p.part, part_id, 0, p.out_w, &xo0, &xo1, &uni);
   if (STEP == 0) uni = false;
   const int ntab = p.same_tables ? 1 : NCO;
 
@@ -524,7 +530,7 @@ __global__ void __launch_bounds__(32 * IWB2_H_WARPS)
   uint64_t *tbar = (uint64_t *)(ord_s + 64);
   int *last_s = (int *)(tbar + 2);                                              // general path: [nout]
 
-  const int grp = blockIdx.y * IWB2_H_WARPS + warp;             // row group of this warp
+  const int grp = rowblock * IWB2_H_WARPS + warp;               // row group of this warp
   const int jb = p.row_lo + grp * 32;
   const bool active = jb < p.row_hi;
   const int y = jb + lane;
