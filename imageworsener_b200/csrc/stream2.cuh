@@ -67,6 +67,25 @@
 #ifndef IWB2_DEFER_H
 #define IWB2_DEFER_H 1
 #endif
+// Uniform path: the first product of an output is ASSIGNED to its accumulator instead of being added to a zeroed one
+// (one DADD and the zeroing less per output and column; with deferred adds two DADDs less).  `+0.0 + x` and `x` differ
+// only for x = -0.0, and an accumulator that starts as -0.0 where the reference has +0.0 meets it again at the first
+// tap whose product is not -0.0: a tap with a positive weight (every normalised window has one) on a sample that is
+// >= +0 -- colour tables and premultiplied samples are never negative and the vertical pass never produces -0.0f for
+// that reason -- so the vertical sums are bit-identical; a horizontal sum could at most end as -0.0 instead of +0.0
+// (all samples of the window exact zeros), which clamps, compares and quantises like +0.0.
+#ifndef IWB2_FIRST_ASSIGN
+#define IWB2_FIRST_ASSIGN 1
+#endif
+// the slot whose output takes its first tap at row r of a uniform cycle (the slot emitted after row r-1), or -1
+__host__ __device__ constexpr int iwb2_first_slot(int r, int S, int stepq) {
+  return IWB2_FIRST_ASSIGN && r % stepq == 0 ? (r / stepq + S - 1) % S : -1;
+}
+// Horizontal uniform path: the epilogues of two adjacent pixels are evaluated together (twice the independent FP32
+// decision chains per basic block; the kernel is latency-bound there at 3 warps per scheduler)
+#ifndef IWB2_H_PAIR
+#define IWB2_H_PAIR 1
+#endif
 #ifndef IWB2_OST_PITCH
 #define IWB2_OST_PITCH 100       // bytes per output staging row (25 words, odd: lane-private banks); <= 96 bytes staged
 #endif

@@ -251,7 +251,10 @@ __global__ void __launch_bounds__(32 * iwb2_v_warps(S, D16), iwb2_v_minb2(S, D16
   };
   // one input row: drain last row's products into the accumulators, form this row's products (deferred), and
   // replace each column's value by the next row's as soon as its products are formed
-  auto taps = [&](double (&vc)[4], const word &xn, unsigned wrow) {
+  // `first` / `second` (uniform path only, compile-time constants after unrolling; -1 elsewhere): the slot whose output
+  // takes its FIRST tap at this row / took it at the row before.  A first product is assigned instead of added to a
+  // zeroed accumulator (see IWB2_FIRST_ASSIGN in stream2.cuh for why the bytes cannot change).
+  auto taps = [&](double (&vc)[4], const word &xn, unsigned wrow, int first, int second) {
     double2 w[SS / 2];
 #pragma unroll
     for (int s2 = 0; s2 < SS / 2; s2++) w[s2] = s2_ldsw(wrow + 16 * s2);
@@ -259,11 +262,14 @@ __global__ void __launch_bounds__(32 * iwb2_v_warps(S, D16), iwb2_v_minb2(S, D16
     for (int c = 0; c < 4; c++) {
 #pragma unroll
       for (int s = 0; s < S; s++) {
+        const double wv = (s & 1) ? w[s >> 1].y : w[s >> 1].x;
         if (IWB2_DEFER_V) {
-          acc[s][c] = __dadd_rn(acc[s][c], prod[s][c]);
-          prod[s][c] = __dmul_rn(vc[c], (s & 1) ? w[s >> 1].y : w[s >> 1].x);
+          if (s == second) acc[s][c] = prod[s][c];
+          else if (s != first) acc[s][c] = __dadd_rn(acc[s][c], prod[s][c]);
+          prod[s][c] = __dmul_rn(vc[c], wv);
         } else {
-          acc[s][c] = __dadd_rn(acc[s][c], __dmul_rn(vc[c], (s & 1) ? w[s >> 1].y : w[s >> 1].x));
+          if (s == first) acc[s][c] = __dmul_rn(vc[c], wv);
+          else acc[s][c] = __dadd_rn(acc[s][c], __dmul_rn(vc[c], wv));
         }
       }
       vc[c] = lookup1(xn, c);
@@ -275,9 +281,9 @@ __global__ void __launch_bounds__(32 * iwb2_v_warps(S, D16), iwb2_v_minb2(S, D16
   // the horizontal kernel's tiles on 16-byte boundaries, which its TMA loads need; here it only splits the store.
   float *outp = p.inter + (ptrdiff_t)(o0 - p.row_base) * p.pitch + SH + col0;   // this thread's 4 floats of row o0
   const ptrdiff_t out_step = p.pitch;
-  auto finish = [&](int k, int o) {
+  auto finish = [&](int k, int o, bool restart) {
 #pragma unroll
-    for (int c = 0; c < 4; c++) if (IWB2_DEFER_V) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
+    for (int c = 0; c < 4; c++) if (IWB2_DEFER_V) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); if (restart) prod[k][c] = 0.0; }
     if (o >= o0 && o < o1) {                                    // emitted rows are consecutive: outp walks down the plane
       const float f0 = (float)acc[k][0], f1 = (float)acc[k][1], f2 = (float)acc[k][2], f3 = (float)acc[k][3];
       if (full && D16 && SH == 0) {
@@ -301,8 +307,10 @@ __global__ void __launch_bounds__(32 * iwb2_v_warps(S, D16), iwb2_v_minb2(S, D16
       }
       outp += out_step;
     }
+    if (restart) {
 #pragma unroll
-    for (int c = 0; c < 4; c++) acc[k][c] = 0.0;
+      for (int c = 0; c < 4; c++) acc[k][c] = 0.0;
+    }
   };
 
   if (STEP > 0 && uni) {
@@ -328,8 +336,8 @@ __global__ void __launch_bounds__(32 * iwb2_v_warps(S, D16), iwb2_v_minb2(S, D16
         if (r == GU - 2) s2_mbar_wait(bar0 + 8 * nslot, npar);  // the last two rows prefetch from the next stage
         const word xcur = xn;
         xn = ring_word(r + 2 < GU ? sb + (r + 2) * TW : sbn + (r + 2 - GU) * TW);   // row r+2
-        taps(vc, xcur, wb + r * SS * 8);                        // row r (values of row r+1 from xcur)
-        if ((r + 1) % STEPQ == 0) finish((r + 1) / STEPQ - 1, og + (r + 1) / STEPQ - 1);
+        taps(vc, xcur, wb + r * SS * 8, iwb2_first_slot(r, S, STEPQ), iwb2_first_slot((r + GU - 1) % GU, S, STEPQ));   // row r (values of row r+1 from xcur)
+        if ((r + 1) % STEPQ == 0) finish((r + 1) / STEPQ - 1, og + (r + 1) / STEPQ - 1, !IWB2_FIRST_ASSIGN);
       }
       __syncwarp();
       if (cyc + NSTU <= ncyc) fill_u(cyc + NSTU, slot);
@@ -374,7 +382,7 @@ __global__ void __launch_bounds__(32 * iwb2_v_warps(S, D16), iwb2_v_minb2(S, D16
   word xn = next_word();                                        // row 1
   int i = 0;                                                    // row being consumed (relative to r0)
   auto row_step = [&]() {
-    taps(vc, xn, pw);
+    taps(vc, xn, pw, -1, -1);
     xn = next_word();                                           // row i+2
     pw += SS * 8;
     if (pw == pw_end) {
@@ -391,7 +399,7 @@ __global__ void __launch_bounds__(32 * iwb2_v_warps(S, D16), iwb2_v_minb2(S, D16
       if (o >= ob && o < o1) {                                  // warp-uniform
         const int iend = last_s[o - ob];
         while (i <= iend) row_step();
-        finish(k, o);
+        finish(k, o, true);
       }
     }
   }
@@ -573,7 +581,14 @@ __global__ void
       s2_bulk_g2s(dst + 32 * TPU * 4, p.sc.w + (ptrdiff_t)(B0 + n * GU) * SS, GU * SS * 8, bar);
     }
   };
-  // prologue: start this warp's pipeline and the (asynchronous) copy of the decision tables, then the small loops
+  // prologue: the (asynchronous) copy of the decision tables, this warp's pipeline, then the small loops
+  if (threadIdx.x == 0) {
+    const unsigned tb = s2_addr(tbar);
+    s2_mbar_init(tb, 1);
+    s2_fence_async();
+    s2_mbar_expect(tb, (unsigned)ntab * IWB2_TAB_BYTES);
+    for (int k = 0; k < ntab; k++) s2_bulk_g2s(s2_addr(tab_s + (size_t)k * IWB2_TAB_BYTES), p.q[k].blob, IWB2_TAB_BYTES, tb);
+  }
   if (active) {
     if (lane == 0) {
 #pragma unroll
@@ -590,13 +605,6 @@ __global__ void
       for (int s = 0; s < NST; s++)
         if (s < nstg) fill(s, s);
     }
-  }
-  if (threadIdx.x == 0) {
-    const unsigned tb = s2_addr(tbar);
-    s2_mbar_init(tb, 1);
-    s2_fence_async();
-    s2_mbar_expect(tb, (unsigned)ntab * IWB2_TAB_BYTES);
-    for (int k = 0; k < ntab; k++) s2_bulk_g2s(s2_addr(tab_s + (size_t)k * IWB2_TAB_BYTES), p.q[k].blob, IWB2_TAB_BYTES, tb);
   }
   for (int i = threadIdx.x; i < 64; i += blockDim.x)
     ord_s[i] = ((float)iwb2_ord[(p.ch[0].dsubtype == 1 ? 64 : 0) + i] + 0.5f) / 64.0f;   // exact in float
@@ -637,7 +645,8 @@ __global__ void
   }
 
   // one input pixel column; nf[] = the next column's samples (already on their way from shared memory)
-  auto taps = [&](double (&vc)[NCH], const float (&nf)[NCH], unsigned wrow) {
+  // (`first` / `second`: as in the vertical kernel)
+  auto taps = [&](double (&vc)[NCH], const float (&nf)[NCH], unsigned wrow, int first, int second) {
     double2 w[SS / 2];
 #pragma unroll
     for (int s2 = 0; s2 < SS / 2; s2++) w[s2] = s2_ldsw(wrow + 16 * s2);
@@ -645,11 +654,14 @@ __global__ void
     for (int c = 0; c < NCH; c++) {
 #pragma unroll
       for (int s = 0; s < S; s++) {
+        const double wv = (s & 1) ? w[s >> 1].y : w[s >> 1].x;
         if (DEFER) {
-          acc[s][c] = __dadd_rn(acc[s][c], prod[s][c]);
-          prod[s][c] = __dmul_rn(vc[c], (s & 1) ? w[s >> 1].y : w[s >> 1].x);
+          if (s == second) acc[s][c] = prod[s][c];
+          else if (s != first) acc[s][c] = __dadd_rn(acc[s][c], prod[s][c]);
+          prod[s][c] = __dmul_rn(vc[c], wv);
         } else {
-          acc[s][c] = __dadd_rn(acc[s][c], __dmul_rn(vc[c], (s & 1) ? w[s >> 1].y : w[s >> 1].x));
+          if (s == first) acc[s][c] = __dmul_rn(vc[c], wv);
+          else acc[s][c] = __dadd_rn(acc[s][c], __dmul_rn(vc[c], wv));
         }
       }
       vc[c] = (double)nf[c];                                    // next column, in place
@@ -665,51 +677,78 @@ __global__ void
              (upto - staged_from) * NCO, min(32, p.row_hi - jb), walign, lane);
     staged_from = upto;
   };
-  // slot k is complete: add its pending products, quantise + dither, stage the bytes, restart the slot
-  auto finish = [&](int k, int xo) {
+  // quantise + dither NP (1 or 2) adjacent output pixels xo, xo+1 whose sums are sv[0], sv[1], and stage their bytes.
+  // The decision chains of all their channels sit in one basic block (no branch between them), so their table lookups
+  // overlap; one warp vote covers the rare samples that need the exact decision.  valid1: pixel xo+1 is inside the
+  // segment (the last pixel of an odd-width image has no partner).
+  auto emit = [&](const double (&sv)[2][NCH], int xo, int np, bool valid1) {
+    if (xo - staged_from >= FU) flush(xo);
+    const unsigned dstb = ost_a + (xo - staged_from) * NCO;
+    float t[2][NCO];
+    uint32_t draw[2][NCO];
+    int code[2][NCO], qg[2][NCO];
+    bool sure[2][NCO], all_sure = true;
 #pragma unroll
-    for (int c = 0; c < NCH; c++) if (DEFER) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); prod[k][c] = 0.0; }
-    if (xo >= xo0 && xo < xo1) {
-      if (xo - staged_from >= FU) flush(xo);
-      const unsigned dstb = ost_a + (xo - staged_from) * NCO;
-      float t[NCO];
-      uint32_t draw[NCO];
-      int code[NCO], qg[NCO];
-      bool sure[NCO], all_sure = true;
+    for (int q = 0; q < 2; q++) {
+      if (q >= np) continue;
 #pragma unroll
       for (int c = 0; c < NCO; c++) {
         const int ci = NCO == NCH ? c : 0;                       // the intermediate channel behind output channel c
         if (NCO != NCH && EPI != 4 && c > 0) {                   // same sample, same threshold: same code
-          t[c] = t[0]; draw[c] = 0; code[c] = code[0]; sure[c] = sure[0]; qg[c] = qg[0];
+          t[q][c] = t[q][0]; draw[q][c] = 0; code[q][c] = code[q][0]; sure[q][c] = sure[q][0]; qg[q][c] = qg[q][0];
           continue;
         }
-        t[c] = EPI == 3 ? s2_ldsf(ord_a + 4 * (xo & 7)) : 0.5f;
-        draw[c] = 0;
-        if (EPI == 4) {
-          draw[c] = iwb_prng_draw_of(rng[c]);
+        t[q][c] = EPI == 3 ? s2_ldsf(ord_a + 4 * ((xo + q) & 7)) : 0.5f;
+        draw[q][c] = 0;
+        if (EPI == 4 && (q == 0 || valid1)) {                    // (warp-uniform: draws are consumed by stored pixels only)
+          draw[q][c] = iwb_prng_draw_of(rng[c]);
           rng[c] = iwb_prng_step(rng[c]);
-          t[c] = (float)draw[c] * (1.0f / 4294967295.0f);
+          t[q][c] = (float)draw[q][c] * (1.0f / 4294967295.0f);
         }
-        code[c] = quantise8_try<EPI>(tab_c[c], qmargin[c], qtop[c], t[c], acc[k][ci], &sure[c], &qg[c]);
-        all_sure = all_sure && sure[c];
+        code[q][c] = quantise8_try<EPI>(tab_c[c], qmargin[c], qtop[c], t[q][c], sv[q][ci], &sure[q][c], &qg[q][c]);
+        all_sure = all_sure && (sure[q][c] || (q == 1 && !valid1));
       }
-      if (__any_sync(0xffffffffu, !all_sure)) {                 // a few 1e-4 of the samples: exact FP64 decision
+    }
+    if (__any_sync(0xffffffffu, !all_sure)) {                   // a few 1e-4 of the samples: exact FP64 decision
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        if (q >= np) continue;
 #pragma unroll
         for (int c = 0; c < NCO; c++) {
           const int ci = NCO == NCH ? c : 0;
-          if (NCO != NCH && EPI != 4 && c > 0) { code[c] = code[0]; continue; }
-          if (!sure[c]) {
+          if (NCO != NCH && EPI != 4 && c > 0) { code[q][c] = code[q][0]; continue; }
+          if (!sure[q][c] && (q == 0 || valid1)) {
             const int tb = p.same_tables ? 0 : c;
-            code[c] = exact8_v2<EPI == 1 ? 0 : (EPI == 2 ? 4 : (EPI == 3 ? 1 : 3))>((const double *)(tab_s + (size_t)tb * IWB2_TAB_BYTES + IWB2_TAB_THR),
-                                                                 p.q[tb].top, acc[k][ci], qg[c], t[c], draw[c]);
+            code[q][c] = exact8_v2<EPI == 1 ? 0 : (EPI == 2 ? 4 : (EPI == 3 ? 1 : 3))>((const double *)(tab_s + (size_t)tb * IWB2_TAB_BYTES + IWB2_TAB_THR),
+                                                                   p.q[tb].top, sv[q][ci], qg[q][c], t[q][c], draw[q][c]);
           }
         }
       }
-#pragma unroll
-      for (int c = 0; c < NCO; c++) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dstb + c), "r"(code[c]) : "memory");
     }
 #pragma unroll
-    for (int c = 0; c < NCH; c++) acc[k][c] = 0.0;
+    for (int q = 0; q < 2; q++) {
+      if (q >= np || (q == 1 && !valid1)) continue;
+#pragma unroll
+      for (int c = 0; c < NCO; c++) asm volatile("st.shared.u8 [%0], %1;" ::"r"(dstb + q * NCO + c), "r"(code[q][c]) : "memory");
+    }
+  };
+  // slot k is complete: add its pending products (deferred adds); `restart`: zero the slot for its next output
+  auto drain = [&](int k, bool restart) {
+#pragma unroll
+    for (int c = 0; c < NCH; c++) if (DEFER) { acc[k][c] = __dadd_rn(acc[k][c], prod[k][c]); if (restart) prod[k][c] = 0.0; }
+  };
+  auto finish = [&](int k, int xo, bool restart) {
+    drain(k, restart);
+    if (xo >= xo0 && xo < xo1) {
+      double sv[2][NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; c++) { sv[0][c] = acc[k][c]; sv[1][c] = 0.0; }
+      emit(sv, xo, 1, false);
+    }
+    if (restart) {
+#pragma unroll
+      for (int c = 0; c < NCH; c++) acc[k][c] = 0.0;
+    }
   };
 
   if (STEP > 0 && uni) {
@@ -725,8 +764,10 @@ __global__ void
     auto elem = [](const float4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); };
     ch = lds128(ring0 + rowoff);
     double vc[NCH];
+    double hold[2][NCH];
+    constexpr bool PAIR = IWB2_H_PAIR && S % 2 == 0;
 #pragma unroll
-    for (int c = 0; c < NCH; c++) vc[c] = (double)elem(ch, c);  // column 0 (NCH <= 4: inside the first chunk)
+    for (int c = 0; c < NCH; c++) { vc[c] = (double)elem(ch, c); hold[0][c] = hold[1][c] = 0.0; }   // column 0 (NCH <= 4: inside the first chunk)
     for (int cyc = 0; cyc < ncyc; cyc++) {
       const int nslot = slot + 1 == NSTU ? 0 : slot + 1;
       const unsigned npar = nslot == 0 ? par ^ 1 : par;
@@ -743,8 +784,29 @@ __global__ void
           if (f % 4 == 0) ch = lds128((r + 1 < GU ? sb : sbn) + f * 4);
           nf[c] = elem(ch, f % 4);
         }
-        taps(vc, nf, wb + r * SS * 8);
-        if ((r + 1) % STEPQ == 0) finish((r + 1) / STEPQ - 1, og + (r + 1) / STEPQ - 1);
+        taps(vc, nf, wb + r * SS * 8, iwb2_first_slot(r, S, STEPQ), iwb2_first_slot((r + GU - 1) % GU, S, STEPQ));
+        if ((r + 1) % STEPQ == 0) {
+          const int k = (r + 1) / STEPQ - 1, xo = og + k;
+          if (!PAIR) {
+            finish(k, xo, !IWB2_FIRST_ASSIGN);
+          } else {
+            // pixels are decided two at a time (og and S are even: pixel og + k with k even is the first of its pair,
+            // and a segment starts on a multiple of 4): the even one waits in `hold` for its neighbour
+            drain(k, !IWB2_FIRST_ASSIGN);
+            if (k % 2 == 0) {
+#pragma unroll
+              for (int c = 0; c < NCH; c++) hold[0][c] = acc[k][c];
+            } else {
+#pragma unroll
+              for (int c = 0; c < NCH; c++) hold[1][c] = acc[k][c];
+              if (xo - 1 >= xo0 && xo - 1 < xo1) emit(hold, xo - 1, 2, xo < xo1);
+            }
+            if (!IWB2_FIRST_ASSIGN) {
+#pragma unroll
+              for (int c = 0; c < NCH; c++) acc[k][c] = 0.0;
+            }
+          }
+        }
       }
       __syncwarp();
       if (cyc + NSTU <= ncyc) fill_u(cyc + NSTU, slot);
@@ -786,7 +848,7 @@ __global__ void
     float nf[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; c++) nf[c] = s2_ldsf(pin + 4 * c);
-    taps(vc, nf, pw);
+    taps(vc, nf, pw, -1, -1);
     pin += NCH * 4;
     if (pin == pin_end) advance_load();
     pw += SS * 8;
@@ -804,7 +866,7 @@ __global__ void
       if (o >= xb && o < xo1) {                                 // warp-uniform
         const int iend = last_s[o - xb];
         while (i <= iend) col_step();
-        finish(k, o);
+        finish(k, o, true);
       }
     }
   }
