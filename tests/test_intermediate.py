@@ -84,7 +84,11 @@ def test_fp32_intermediate_is_bit_identical_to_oracle(prod, oracle_port, case):
         tight, rows = rows, padded
     else:
         tight = rows
+    _check_planes(prod, cfg, rows, tight, opts)
 
+
+def _check_planes(prod, cfg, rows, tight, opts):
+    iw, ih, ow, oh = cfg.in_w, cfg.in_h, cfg.out_w, cfg.out_h
     # oracle: last processed channel's plane
     from oracle_port import OraclePort
     olib = OraclePort()
@@ -127,6 +131,42 @@ def test_fp32_intermediate_is_bit_identical_to_oracle(prod, oracle_port, case):
     bad = np.argwhere(want.view(np.uint32) != got.view(np.uint32))
     detail = "; ".join(f"(row {j}, col {i}): oracle {want[j, i]!r} cuda {got[j, i]!r}" for j, i in bad[:6])
     assert len(bad) == 0, f"{len(bad)} of {got.size} FP32 intermediate samples differ: {detail}"
+
+
+# ---- the sign of zero ---------------------------------------------------------------------------------------------
+# The uniform paths assign an output's first product instead of adding it to a zeroed accumulator (stream2.cuh:
+# IWB2_FIRST_ASSIGN).  A black sample under a negative filter lobe makes that product -0.0 where the reference holds
+# +0.0 + -0.0 = +0.0; the next tap with a positive weight brings the sum back to +0.0, so the FP32 planes must stay
+# bit-identical -- including the sign of their zeros -- on images with black regions, rows and columns.
+ZERO_CASES = [
+    ("black_down2_lanczos_rgb", 512, 384, RGB, 8, 256, 192, "-filter lanczos -dither o", {}),
+    ("black_down3_catrom_holes", 480, 360, RGB, 8, 160, 120, "-filter catrom -dither o", {}),
+    ("black_down2_gray_as_rgb", 512, 384, GRAY, 8, 256, 192, "-filter lanczos -dither r", {}),
+    ("black_rgb16_stream", 320, 200, RGB, 16, 160, 100, "-filter lanczos -dither o", {}),
+    ("black_down4_mitchell_gray", 512, 384, GRAY, 8, 128, 96, "-filter mitchell -grayscale", {}),
+    ("black_rgba8_down2_gather", 400, 300, L.IW_IMGTYPE_RGBA, 8, 200, 150, "-filter catrom -bkgd 246", {}),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pattern", ["all", "blocks", "stripes"])
+@pytest.mark.parametrize("case", ZERO_CASES, ids=lambda c: c[0])
+def test_black_regions_keep_the_sign_of_zero(prod, oracle_port, case, pattern):
+    name, iw, ih, typ, depth, ow, oh, extra, opts = case
+    cfg = configs.Config(name, iw, ih, typ, depth, ow, oh, f"-width {ow} -height {oh} {extra}")
+    rows = configs.synth_rows(prod, cfg).copy()
+    bpp = L.imgtype_num_channels(typ) * depth // 8
+    if pattern == "all":
+        rows[:] = 0
+    elif pattern == "blocks":                    # black rectangles with noise around them (and noise islands inside)
+        rows[ih // 5: ih // 2, (iw // 6) * bpp: (iw // 2) * bpp] = 0
+        rows[ih // 2 + 7:, : (iw // 3) * bpp] = 0
+        rows[ih // 2 + 40: ih // 2 + 43, (iw // 8) * bpp: (iw // 8 + 2) * bpp] = 0xc8
+    else:                                        # single black rows / columns between noise
+        rows[::7] = 0
+        px = rows.reshape(ih, iw, bpp)
+        px[:, ::5] = 0
+    _check_planes(prod, cfg, rows, rows, opts)
 
 
 # ---- the same comparison against the UNMODIFIED reference build --------------------------------------------------
