@@ -70,6 +70,27 @@ def ncu_traffic(kernel_class: str):
     return d.get(kernel_class), f"ncu --set full capture, commit {d.get('commit')}"
 
 
+def ncu_issue_cycles(kernel_classes, n_sm=148):
+    """Issue-port cycles per scheduler that the captured launches of these kernel classes need: an FP64 warp instruction
+    holds a scheduler's issue port for two cycles, any other instruction for one (measured: tools/issue_probe.cu,
+    profiles/r2h_issue_probe.txt -- a DMUL+DADD pair plus NX independent FADDs costs 4 + NX cycles, not max(4, 2 + NX)).
+    Instruction counts come from the same stamped capture as `traffic`; None when HEAD's kernels differ."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p))
+    except Exception:  # noqa: BLE001
+        return None
+    if d.get("kernel_sources_sha") != kernel_sources_sha():
+        return None
+    total = 0.0
+    for k in kernel_classes:
+        n, f = d.get(k + "_warp_instr"), d.get(k + "_warp_instr_fp64")
+        if n is None or f is None:
+            return None
+        total += (n + f) / (4.0 * n_sm)
+    return total
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -679,6 +700,15 @@ def main():
                          "hbm_frac_ceiling": (alg_bytes_step / peak / 1e9) / (2.0 * taps / FP64_PEAK_LANE_INSTR)},
                 "note": "every tap is one DMUL + one DADD (FMA forbidden by bit-exactness): the FP64 pipe binds before "
                         "HBM, `fp64.hbm_frac_ceiling` is the HBM fraction at 100 % FP64 issue; see DESIGN.md"}
+    issue_cycles = ncu_issue_cycles(list(stats)) if args.config == "cfg2" else None
+    if issue_cycles:
+        # the tighter roof for these kernels: issue-port cycles (2 per FP64 instruction, 1 per other) of the step's
+        # captured instruction streams against the step's cycles at the SM clock sampled during the timed region
+        mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+        roofline["issue_port"] = {"cycles_needed_per_scheduler": issue_cycles, "cycles_elapsed": ms_per_step * 1e-3 * mhz * 1e6,
+                                  "frac": issue_cycles / (ms_per_step * 1e-3 * mhz * 1e6),
+                                  "model": "2 issue cycles per FP64 warp instruction + 1 per other (tools/issue_probe.cu); "
+                                           "instruction counts from the stamped ncu capture"}
     dll.iwb200_job_destroy(job)
     lib.iw_destroy_context(ctx)
 

@@ -15,6 +15,7 @@ WANT = ['gpu__time_duration.sum', 'sm__cycles_elapsed.avg', 'dram__bytes_read.su
         'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio']
 rep = sys.argv[1]
+traffic_record = None
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -39,7 +40,7 @@ if '--traffic' in sys.argv:      # record DRAM bytes per launch for bench.py's r
     d['kernel_sources_sha'] = sha
     d['commit'] = subprocess.run(['git', '-C', root, 'rev-parse', '--short', 'HEAD'], capture_output=True, text=True).stdout.strip()
     d[cls] = num('dram__bytes_read.sum') + num('dram__bytes_write.sum')
-    json.dump(d, open(tp, 'w'), indent=1)
+    traffic_record = (tp, d, cls)
     sys.argv.remove('--traffic')
 for w in WANT:
     if w in hdr:
@@ -55,6 +56,12 @@ for r in data:
     t = r[isrc].split()
     op = (t[1] if t[0].startswith('@') else t[0]).split('.')[0]
     ops[op] += int(r[iex]); st[op] += int(r[ist])
+if traffic_record:               # warp instructions per launch, all and FP64 (DADD / DMUL / DFMA / DSETP): bench.py's issue-port model
+    import json
+    tp, d, cls = traffic_record
+    d[cls + '_warp_instr'] = tot
+    d[cls + '_warp_instr_fp64'] = sum(v for k, v in ops.items() if k in ('DADD', 'DMUL', 'DFMA', 'DSETP', 'DMNMX'))
+    json.dump(d, open(tp, 'w'), indent=1)
 print('  SASS instructions executed:', tot)
 for k, v in ops.most_common(14):
     print(f'    {k:9s} {100 * v / tot:5.1f}%   stall samples {st[k]}')
