@@ -145,6 +145,9 @@ ZERO_CASES = [
     ("black_rgb16_stream", 320, 200, RGB, 16, 160, 100, "-filter lanczos -dither o", {}),
     ("black_down4_mitchell_gray", 512, 384, GRAY, 8, 128, 96, "-filter mitchell -grayscale", {}),
     ("black_rgba8_down2_gather", 400, 300, L.IW_IMGTYPE_RGBA, 8, 200, 150, "-filter catrom -bkgd 246", {}),
+    ("black_rgba16_up_gather", 200, 150, L.IW_IMGTYPE_RGBA, 16, 500, 380, "-filter mitchell -bkgd 369", {}),
+    ("black_ga8_down_gather", 400, 300, L.IW_IMGTYPE_GRAYA, 8, 260, 200, "-filter catrom", {}),
+    ("black_rgba8_down3_tile", 420, 300, L.IW_IMGTYPE_RGBA, 8, 140, 100, "-filter catrom -bkgd 246", {}),
 ]
 
 
